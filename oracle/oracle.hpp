@@ -1,0 +1,1077 @@
+// oracle/oracle.hpp — TEST INFRASTRUCTURE ONLY.
+//
+// CPU restatement (C++17 + OpenMP, FP64, compiled with -ffp-contract=off) of the
+// reference's short-range LJ MD step.  It is the CHECKER for the CUDA product
+// path; nothing under cabanamd_b200/ may include, link or call it.  Only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs use it.
+//
+// Parity status: the real reference (Kokkos 4.3.01 + Cabana 0.6.1 + MPI) cannot
+// be compiled in this image, so this restatement is pinned by
+//   (1) the reference's own tstNeighbor criterion (O(N^2) brute force,
+//       d^2 <= rc^2, i != j, ghost rows empty)           unit_test/tstNeighbor.hpp:76-190
+//   (2) the reference's tstIntegrator reversibility check unit_test/tstIntegrator.hpp:83-137
+//   (3) physics known answers derived from the reference formulas (in.lj step 0:
+//       T=1.400000, PotE=-6.332812, ETot=-4.232820)
+// Force / energy / comm outputs have no golden vectors in the reference tree:
+// for those rows parity is "unpinned by the reference's tests" (SURVEY.md 8c).
+//
+// Every function cites the reference file:line it follows (paths relative to
+// /root/reference/src unless stated).  [Cabana] marks semantics of the
+// un-vendored Cabana 0.6.1 dependency restated from its published algorithm.
+#pragma once
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace orc
+{
+
+// ---------------------------------------------------------------------------
+// LAMMPS "loop geom" velocity RNG.   inputFile.h:73-148
+// Park-Miller via Schrage; seed = Jenkins one-at-a-time hash over the 4 bytes of
+// the user seed then the 24 bytes of (x,y,z); bytes are added as *signed char*;
+// 27-bit mask (0x7ffffff); 5 warm-up draws.
+// ---------------------------------------------------------------------------
+struct RandomVelocityGeom
+{
+    int seed = 0;
+    double uniform()
+    {
+        const int IA = 16807, IM = 2147483647, IQ = 127773, IR = 2836;
+        const double AM = 1.0 / IM;
+        int k = seed / IQ;
+        seed = IA * ( seed - k * IQ ) - IR * k;
+        if ( seed < 0 )
+            seed += IM;
+        return AM * seed;
+    }
+    void reset( int ibase, const double *coord )
+    {
+        unsigned int hash = 0;
+        const char *str = reinterpret_cast<const char *>( &ibase );
+        for ( int i = 0; i < (int)sizeof( int ); i++ )
+        {
+            hash += (signed char)str[i];
+            hash += ( hash << 10 );
+            hash ^= ( hash >> 6 );
+        }
+        str = reinterpret_cast<const char *>( coord );
+        for ( int i = 0; i < (int)( 3 * sizeof( double ) ); i++ )
+        {
+            hash += (signed char)str[i];
+            hash += ( hash << 10 );
+            hash ^= ( hash >> 6 );
+        }
+        hash += ( hash << 3 );
+        hash ^= ( hash >> 11 );
+        hash += ( hash << 15 );
+        seed = hash & 0x7ffffff;
+        if ( !seed )
+            seed = 1;
+        for ( int i = 0; i < 5; i++ )
+            uniform();
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Domain decomposition.  system.h:149-205,251-271 + [Cabana::Grid]
+// ---------------------------------------------------------------------------
+// [Cabana] DimBlockPartitioner::ranksPerDimension == MPI_Dims_create(n, 3):
+// factors as balanced as possible, non-increasing order.
+inline std::array<int, 3> dims_create( int n )
+{
+    std::array<int, 3> best = { n, 1, 1 };
+    for ( int a = 1; a <= n; a++ )
+    {
+        if ( n % a )
+            continue;
+        for ( int b = 1; b <= n / a; b++ )
+        {
+            if ( ( n / a ) % b )
+                continue;
+            int c = n / a / b;
+            std::array<int, 3> t = { a, b, c };
+            std::sort( t.begin(), t.end(), std::greater<int>() );
+            if ( t[0] - t[2] < best[0] - best[2] ||
+                 ( t[0] - t[2] == best[0] - best[2] && t[0] < best[0] ) )
+                best = t;
+        }
+    }
+    return best;
+}
+
+struct Domain
+{
+    double glo[3], ghi[3], gext[3];   // global box      (global_mesh_*)
+    int grid[3], pos[3];              // ranks_per_dim, rank_dim_pos
+    double llo[3], lhi[3], lext[3];   // local_mesh_lo/hi, local_mesh_*
+    double ghost_lo[3], ghost_hi[3];  // ghost_mesh_lo/hi
+    int halo_cells;                   // halo_width
+};
+
+// system.h:149-192 (create_domain with explicit ghost cutoff) and :251-271.
+// [Cabana::Grid] global mesh of 100*ranks cells per dim split evenly;
+// MPI_Cart rank -> coords with the LAST dimension fastest.
+inline Domain make_domain( const double glo[3], const double ghi[3], int nranks, int rank,
+                           double ghost_cutoff )
+{
+    Domain d;
+    auto g = dims_create( nranks );
+    int r = rank;
+    d.pos[2] = r % g[2];
+    r /= g[2];
+    d.pos[1] = r % g[1];
+    r /= g[1];
+    d.pos[0] = r;
+    double mincell = 1e300;
+    double cell[3];
+    for ( int k = 0; k < 3; k++ )
+    {
+        d.grid[k] = g[k];
+        d.glo[k] = glo[k];
+        d.ghi[k] = ghi[k];
+        d.gext[k] = ghi[k] - glo[k];
+        int ncell = 100 * g[k];
+        cell[k] = ( ghi[k] - glo[k] ) / ncell;
+        mincell = std::min( mincell, cell[k] );
+    }
+    d.halo_cells = (int)std::ceil( ghost_cutoff / mincell );
+    for ( int k = 0; k < 3; k++ )
+    {
+        int off = 100 * d.pos[k];
+        d.llo[k] = glo[k] + cell[k] * off;
+        d.lhi[k] = glo[k] + cell[k] * ( off + 100 );
+        d.lext[k] = d.lhi[k] - d.llo[k];
+        d.ghost_lo[k] = glo[k] + cell[k] * ( off - d.halo_cells );
+        d.ghost_hi[k] = glo[k] + cell[k] * ( off + 100 + d.halo_cells );
+    }
+    return d;
+}
+
+inline int rank_of( const int grid[3], int i, int j, int k )
+{
+    i = ( i % grid[0] + grid[0] ) % grid[0];
+    j = ( j % grid[1] + grid[1] ) % grid[1];
+    k = ( k % grid[2] + grid[2] ) % grid[2];
+    return ( i * grid[1] + j ) * grid[2] + k;
+}
+
+// ---------------------------------------------------------------------------
+// Per-rank particle store (SoA mirror of the 88-byte tuple, system_1aosoa.h:28-29)
+// ---------------------------------------------------------------------------
+struct NeighList
+{
+    std::vector<int> counts;      // [N_local+N_ghost]  (ghost rows 0)
+    std::vector<int64_t> offsets; // [N_local+1]
+    std::vector<int> neigh;       // CSR
+    int max_neigh = 0;
+};
+
+struct Rank
+{
+    Domain dom;
+    int N_local = 0, N_ghost = 0;
+    std::vector<double> x, v, f, q; // x,v,f: [n][3]
+    std::vector<int> type, id;
+    // comm plans kept between rebuilds (comm_mpi.h:76-101)
+    int nbr_send[6], nbr_recv[6];
+    int num_send[6] = { 0 }, num_recv[6] = { 0 };
+    std::vector<int> send_idx[6];
+    NeighList list;
+    // binning results (binning_cabana.h:62-68)
+    int nbin[3] = { 0, 0, 0 };
+    double bmin[3], bmax[3];
+
+    void resize( int n )
+    {
+        x.resize( 3 * (size_t)n );
+        v.resize( 3 * (size_t)n );
+        f.resize( 3 * (size_t)n );
+        q.resize( n );
+        type.resize( n );
+        id.resize( n );
+    }
+    int size() const { return (int)type.size(); }
+};
+
+struct Params
+{
+    int ntypes = 1;
+    std::vector<double> mass = { 1.0 };
+    std::vector<double> lj1, lj2, cutsq; // ntypes x ntypes
+    double boltz = 1.0, mvv2e = 1.0, dt = 0.005;
+    double force_cutoff = 2.5, skin = 0.3;
+    bool half = false;
+    int exchange_rate = 20;
+    double ghost_cutoff = 20.0; // comm_modify cutoff (sizes only the Verlet bounding grid)
+    double neigh_cut() const { return force_cutoff + skin; }
+};
+
+// force_lj_cabana_neigh_impl.h:62-89
+inline void init_coeff( Params &p, int i, int j, double eps, double sigma, double cut )
+{
+    size_t n = (size_t)p.ntypes * p.ntypes;
+    if ( p.lj1.size() != n )
+    {
+        p.lj1.assign( n, 0.0 );
+        p.lj2.assign( n, 0.0 );
+        p.cutsq.assign( n, 0.0 );
+    }
+    double a = 48.0 * eps * std::pow( sigma, 12.0 );
+    double b = 24.0 * eps * std::pow( sigma, 6.0 );
+    p.lj1[i * p.ntypes + j] = p.lj1[j * p.ntypes + i] = a;
+    p.lj2[i * p.ntypes + j] = p.lj2[j * p.ntypes + i] = b;
+    p.cutsq[i * p.ntypes + j] = p.cutsq[j * p.ntypes + i] = cut * cut;
+}
+
+// ---------------------------------------------------------------------------
+// Integrator.  integrator_nve.h:91-110, integrator_nve_impl.h:50-54
+// ---------------------------------------------------------------------------
+inline void initial_integrate( Rank &r, const Params &p )
+{
+    const double dtf = 0.5 * p.dt / p.mvv2e, dtv = p.dt;
+#pragma omp parallel for schedule( static )
+    for ( int i = 0; i < r.N_local; i++ )
+    {
+        const double dtfm = dtf / p.mass[r.type[i]];
+        for ( int d = 0; d < 3; d++ )
+            r.v[3 * i + d] += dtfm * r.f[3 * i + d];
+        for ( int d = 0; d < 3; d++ )
+            r.x[3 * i + d] += dtv * r.v[3 * i + d];
+    }
+}
+inline void final_integrate( Rank &r, const Params &p )
+{
+    const double dtf = 0.5 * p.dt / p.mvv2e;
+#pragma omp parallel for schedule( static )
+    for ( int i = 0; i < r.N_local; i++ )
+    {
+        const double dtfm = dtf / p.mass[r.type[i]];
+        for ( int d = 0; d < 3; d++ )
+            r.v[3 * i + d] += dtfm * r.f[3 * i + d];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Binning.  binning_cabana_impl.h:57-113 + [Cabana] LinkedCellList / permute
+// Grid n_d = floor((max-min)/delta), dx' = (max-min)/n, cell = floor((x-min)/dx')
+// clamped into [0,n-1], cardinal (i*ny+j)*nz+k; stable (ascending old index)
+// inside a cell (the reference's order is atomic-arrival = unspecified).
+// Returns the permutation: new[i] = old[perm[i]].
+// ---------------------------------------------------------------------------
+struct CellGrid
+{
+    double min[3], max[3], rdx[3];
+    int n[3];
+    void init( const double mn[3], const double mx[3], const double delta[3] )
+    {
+        for ( int d = 0; d < 3; d++ )
+        {
+            min[d] = mn[d];
+            max[d] = mx[d];
+            n[d] = (int)std::floor( ( mx[d] - mn[d] ) / delta[d] );
+            if ( n[d] < 1 )
+                n[d] = 1;
+            double dx = ( mx[d] - mn[d] ) / n[d];
+            rdx[d] = 1.0 / dx;
+        }
+    }
+    int cell1( double xv, int d ) const
+    {
+        int c = (int)std::floor( ( xv - min[d] ) * rdx[d] );
+        if ( c < 0 )
+            c = 0;
+        if ( c > n[d] - 1 )
+            c = n[d] - 1;
+        return c;
+    }
+    int cell( const double *xp ) const
+    {
+        return ( cell1( xp[0], 0 ) * n[1] + cell1( xp[1], 1 ) ) * n[2] + cell1( xp[2], 2 );
+    }
+    int ncell() const { return n[0] * n[1] * n[2]; }
+};
+
+inline std::vector<int> create_binning( Rank &r, double dx_in, double dy_in, double dz_in,
+                                        int halo_depth )
+{
+    const double din[3] = { dx_in, dy_in, dz_in };
+    double delta[3];
+    for ( int d = 0; d < 3; d++ )
+    {
+        r.nbin[d] = (int)( r.dom.lext[d] / din[d] );
+        if ( r.nbin[d] == 0 )
+            r.nbin[d] = 1;
+        delta[d] = r.dom.lext[d] / r.nbin[d];
+    }
+    const double eps = delta[0] / 1000;
+    for ( int d = 0; d < 3; d++ )
+    {
+        r.bmin[d] = -delta[d] * halo_depth - eps + r.dom.llo[d];
+        r.bmax[d] = delta[d] * halo_depth + eps + r.dom.lhi[d];
+    }
+    CellGrid g;
+    g.init( r.bmin, r.bmax, delta );
+    const int n = r.N_local;
+    std::vector<int> cell( n ), count( g.ncell() + 1, 0 ), perm( n );
+    for ( int i = 0; i < n; i++ )
+    {
+        cell[i] = g.cell( &r.x[3 * i] );
+        count[cell[i] + 1]++;
+    }
+    for ( int c = 0; c < g.ncell(); c++ )
+        count[c + 1] += count[c];
+    for ( int i = 0; i < n; i++ )
+        perm[count[cell[i]]++] = i;
+    // permute all six fields (system_1aosoa.h:82-85)
+    Rank t;
+    t.resize( n );
+    for ( int i = 0; i < n; i++ )
+    {
+        int o = perm[i];
+        for ( int d = 0; d < 3; d++ )
+        {
+            t.x[3 * i + d] = r.x[3 * o + d];
+            t.v[3 * i + d] = r.v[3 * o + d];
+            t.f[3 * i + d] = r.f[3 * o + d];
+        }
+        t.q[i] = r.q[o];
+        t.type[i] = r.type[o];
+        t.id[i] = r.id[o];
+    }
+    std::copy( t.x.begin(), t.x.end(), r.x.begin() );
+    std::copy( t.v.begin(), t.v.end(), r.v.begin() );
+    std::copy( t.f.begin(), t.f.end(), r.f.begin() );
+    std::copy( t.q.begin(), t.q.end(), r.q.begin() );
+    std::copy( t.type.begin(), t.type.end(), r.type.begin() );
+    std::copy( t.id.begin(), t.id.end(), r.id.begin() );
+    return perm;
+}
+
+// ---------------------------------------------------------------------------
+// Verlet list.  neighbor_verlet.h:43-62 + [Cabana] VerletList
+// Row i in [0,n_local) lists every j in [0,n_total) with isValid(i,j) and
+// dx*dx+dy*dy+dz*dz <= r*r (inclusive, no FMA contraction, left-to-right sum).
+// Full: i != j.  Half: i != j and (xj>xi || (xj==xi && (yj>yi || (yj==yi && zj>zi)))).
+// Candidates come from a cell grid of size r over [grid_min,grid_max] (27-cell
+// stencil clipped at the edges); order inside a row = ascending cell, then
+// ascending index (the reference's order is unspecified).
+// ---------------------------------------------------------------------------
+inline bool pair_valid( bool half, int i, int j, const double *xi, const double *xj )
+{
+    if ( i == j )
+        return false;
+    if ( !half )
+        return true;
+    return xj[0] > xi[0] ||
+           ( xj[0] == xi[0] && ( xj[1] > xi[1] || ( xj[1] == xi[1] && xj[2] > xi[2] ) ) );
+}
+
+inline bool within( const double *xi, const double *xj, double rsqr )
+{
+    const double dx = xi[0] - xj[0];
+    const double dy = xi[1] - xj[1];
+    const double dz = xi[2] - xj[2];
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    return d2 <= rsqr;
+}
+
+inline void neigh_build( const double *x, int n_local, int n_total, double r, bool half,
+                         const double gmin[3], const double gmax[3], NeighList &L )
+{
+    const double rsqr = r * r;
+    const double delta[3] = { r, r, r };
+    CellGrid g;
+    g.init( gmin, gmax, delta );
+    const int nc = g.ncell();
+    std::vector<int> cell( n_total ), start( nc + 1, 0 ), perm( n_total );
+    for ( int i = 0; i < n_total; i++ )
+    {
+        cell[i] = g.cell( x + 3 * i );
+        start[cell[i] + 1]++;
+    }
+    for ( int c = 0; c < nc; c++ )
+        start[c + 1] += start[c];
+    {
+        std::vector<int> cur( start.begin(), start.end() - 1 );
+        for ( int i = 0; i < n_total; i++ )
+            perm[cur[cell[i]]++] = i;
+    }
+    L.counts.assign( n_total, 0 );
+    L.offsets.assign( n_local + 1, 0 );
+    auto visit = [&]( int i, auto &&fn )
+    {
+        const double *xi = x + 3 * i;
+        int ci[3] = { g.cell1( xi[0], 0 ), g.cell1( xi[1], 1 ), g.cell1( xi[2], 2 ) };
+        for ( int a = std::max( ci[0] - 1, 0 ); a <= std::min( ci[0] + 1, g.n[0] - 1 ); a++ )
+            for ( int b = std::max( ci[1] - 1, 0 ); b <= std::min( ci[1] + 1, g.n[1] - 1 ); b++ )
+                for ( int c = std::max( ci[2] - 1, 0 ); c <= std::min( ci[2] + 1, g.n[2] - 1 );
+                      c++ )
+                {
+                    int cc = ( a * g.n[1] + b ) * g.n[2] + c;
+                    for ( int s = start[cc]; s < start[cc + 1]; s++ )
+                    {
+                        int j = perm[s];
+                        if ( pair_valid( half, i, j, xi, x + 3 * j ) &&
+                             within( xi, x + 3 * j, rsqr ) )
+                            fn( j );
+                    }
+                }
+    };
+#pragma omp parallel for schedule( dynamic, 256 )
+    for ( int i = 0; i < n_local; i++ )
+    {
+        int c = 0;
+        visit( i, [&]( int ) { c++; } );
+        L.counts[i] = c;
+    }
+    int mx = 0;
+    for ( int i = 0; i < n_local; i++ )
+    {
+        L.offsets[i + 1] = L.offsets[i] + L.counts[i];
+        mx = std::max( mx, L.counts[i] );
+    }
+    L.max_neigh = mx;
+    L.neigh.resize( (size_t)L.offsets[n_local] );
+#pragma omp parallel for schedule( dynamic, 256 )
+    for ( int i = 0; i < n_local; i++ )
+    {
+        int64_t o = L.offsets[i];
+        visit( i, [&]( int j ) { L.neigh[o++] = j; } );
+    }
+}
+
+// O(N^2) restatement of unit_test/tstNeighbor.hpp:76-141 (+ half discriminator)
+inline void neigh_brute( const double *x, int n_local, int n_total, double r, bool half,
+                         NeighList &L )
+{
+    const double rsqr = r * r;
+    L.counts.assign( n_total, 0 );
+    L.offsets.assign( n_local + 1, 0 );
+    L.neigh.clear();
+    for ( int i = 0; i < n_local; i++ )
+    {
+        for ( int j = 0; j < n_total; j++ )
+            if ( pair_valid( half, i, j, x + 3 * i, x + 3 * j ) &&
+                 within( x + 3 * i, x + 3 * j, rsqr ) )
+            {
+                L.neigh.push_back( j );
+                L.counts[i]++;
+            }
+        L.offsets[i + 1] = L.offsets[i] + L.counts[i];
+        L.max_neigh = std::max( L.max_neigh, L.counts[i] );
+    }
+}
+
+// ---------------------------------------------------------------------------
+// LJ force / energy.  force_lj_cabana_neigh_impl.h:151-377
+// The reference lambda does f(i) += per pair into a pre-zeroed array, i.e. the
+// sum runs in list order starting from the existing f(i).
+// ---------------------------------------------------------------------------
+inline void force_full( const double *x, const int *type, double *f, int n_local,
+                        const NeighList &L, const Params &p )
+{
+#pragma omp parallel for schedule( dynamic, 256 )
+    for ( int i = 0; i < n_local; i++ )
+    {
+        const double xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+        const int ti = type[i];
+        double fx = f[3 * i], fy = f[3 * i + 1], fz = f[3 * i + 2];
+        for ( int64_t k = L.offsets[i]; k < L.offsets[i + 1]; k++ )
+        {
+            const int j = L.neigh[k];
+            const double dx = xi - x[3 * j], dy = yi - x[3 * j + 1], dz = zi - x[3 * j + 2];
+            const int tj = type[j];
+            const double rsq = dx * dx + dy * dy + dz * dz;
+            if ( rsq < p.cutsq[ti * p.ntypes + tj] )
+            {
+                const double r2inv = 1.0 / rsq;
+                const double r6inv = r2inv * r2inv * r2inv;
+                const double fpair = ( r6inv * ( p.lj1[ti * p.ntypes + tj] * r6inv -
+                                                 p.lj2[ti * p.ntypes + tj] ) ) *
+                                     r2inv;
+                fx += dx * fpair;
+                fy += dy * fpair;
+                fz += dz * fpair;
+            }
+        }
+        f[3 * i] = fx;
+        f[3 * i + 1] = fy;
+        f[3 * i + 2] = fz;
+    }
+}
+
+// Serial on purpose: the j-side updates make the sum order matter and the
+// oracle must be deterministic.  force_lj_cabana_neigh_impl.h:205-259
+inline void force_half( const double *x, const int *type, double *f, int n_local,
+                        const NeighList &L, const Params &p )
+{
+    for ( int i = 0; i < n_local; i++ )
+    {
+        const double xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+        const int ti = type[i];
+        for ( int64_t k = L.offsets[i]; k < L.offsets[i + 1]; k++ )
+        {
+            const int j = L.neigh[k];
+            const double dx = xi - x[3 * j], dy = yi - x[3 * j + 1], dz = zi - x[3 * j + 2];
+            const int tj = type[j];
+            const double rsq = dx * dx + dy * dy + dz * dz;
+            if ( rsq < p.cutsq[ti * p.ntypes + tj] )
+            {
+                const double r2inv = 1.0 / rsq;
+                const double r6inv = r2inv * r2inv * r2inv;
+                const double fpair = ( r6inv * ( p.lj1[ti * p.ntypes + tj] * r6inv -
+                                                 p.lj2[ti * p.ntypes + tj] ) ) *
+                                     r2inv;
+                f[3 * i] += dx * fpair;
+                f[3 * i + 1] += dy * fpair;
+                f[3 * i + 2] += dz * fpair;
+                f[3 * j] -= dx * fpair;
+                f[3 * j + 1] -= dy * fpair;
+                f[3 * j + 2] -= dz * fpair;
+            }
+        }
+    }
+}
+
+// force_lj_cabana_neigh_impl.h:261-377.  fac = 0.5 (full); half: 1 if j<N_local
+// else 0.5 (reference formula); corrected!=0 uses fac=1
+// for every stored half-list pair.
+inline double energy( const double *x, const int *type, int n_local, const NeighList &L,
+                      const Params &p, bool half, bool corrected = false )
+{
+    double PE = 0.0;
+#pragma omp parallel for schedule( static ) reduction( + : PE )
+    for ( int i = 0; i < n_local; i++ )
+    {
+        const double xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+        const int ti = type[i];
+        for ( int64_t k = L.offsets[i]; k < L.offsets[i + 1]; k++ )
+        {
+            const int j = L.neigh[k];
+            const double dx = xi - x[3 * j], dy = yi - x[3 * j + 1], dz = zi - x[3 * j + 2];
+            const int tj = type[j];
+            const double rsq = dx * dx + dy * dy + dz * dz;
+            const double cutsq = p.cutsq[ti * p.ntypes + tj];
+            if ( rsq < cutsq )
+            {
+                const double lj1 = p.lj1[ti * p.ntypes + tj], lj2 = p.lj2[ti * p.ntypes + tj];
+                const double r2inv = 1.0 / rsq;
+                const double r6inv = r2inv * r2inv * r2inv;
+                double fac = 0.5;
+                if ( half )
+                    fac = ( j < n_local || corrected ) ? 1.0 : 0.5;
+                PE += fac * r6inv * ( 0.5 * lj1 * r6inv - lj2 ) / 6.0;
+                const double r2invc = 1.0 / cutsq;
+                const double r6invc = r2invc * r2invc * r2invc;
+                PE -= fac * r6invc * ( 0.5 * lj1 * r6invc - lj2 ) / 6.0;
+            }
+        }
+    }
+    return PE;
+}
+
+// property_temperature.h:73-79 / property_kine.h:72-78: sum m v^2 over locals
+inline double sum_mv2( const Rank &r, const Params &p )
+{
+    double s = 0.0;
+    for ( int i = 0; i < r.N_local; i++ )
+        s += ( r.v[3 * i] * r.v[3 * i] + r.v[3 * i + 1] * r.v[3 * i + 1] +
+               r.v[3 * i + 2] * r.v[3 * i + 2] ) *
+             p.mass[r.type[i]];
+    return s;
+}
+
+// ---------------------------------------------------------------------------
+// The simulation over R in-process "virtual ranks" (stand-in for MPI ranks).
+// ---------------------------------------------------------------------------
+struct Thermo
+{
+    int step;
+    double T, PE, KE;
+};
+
+struct Sim
+{
+    Params p;
+    std::vector<Rank> ranks;
+    int N = 0; // global atom count
+    int step = 0;
+    std::vector<Thermo> thermo;
+    double t_force = 0, t_neigh = 0, t_comm = 0, t_int = 0, t_other = 0;
+
+    int nranks() const { return (int)ranks.size(); }
+
+    // comm_mpi_impl.h:78-119
+    void create_domain_decomposition()
+    {
+        for ( auto &r : ranks )
+        {
+            const int *g = r.dom.grid, *q = r.dom.pos;
+            r.nbr_send[0] = rank_of( g, q[0] + 1, q[1], q[2] );
+            r.nbr_send[1] = rank_of( g, q[0] - 1, q[1], q[2] );
+            r.nbr_send[2] = rank_of( g, q[0], q[1] + 1, q[2] );
+            r.nbr_send[3] = rank_of( g, q[0], q[1] - 1, q[2] );
+            r.nbr_send[4] = rank_of( g, q[0], q[1], q[2] + 1 );
+            r.nbr_send[5] = rank_of( g, q[0], q[1], q[2] - 1 );
+            for ( int ph = 0; ph < 6; ph++ )
+                r.nbr_recv[ph] = r.nbr_send[ph ^ 1];
+        }
+    }
+
+    // inputFile_impl.h:536-868 (fcc branch): lattice fill, ids via scan, hashed-RNG
+    // velocities, momentum zeroing, temperature rescale.
+    void create_lattice_fcc( double lattice_constant, const double blo[3], const double bhi[3],
+                             int nr, double temp, int seed )
+    {
+        const double a = lattice_constant;
+        double glo[3], ghi[3];
+        for ( int d = 0; d < 3; d++ )
+        {
+            glo[d] = a * blo[d];
+            ghi[d] = a * bhi[d];
+        }
+        ranks.assign( nr, Rank() );
+        const double basis[4][3] = {
+            { 0.0, 0.0, 0.0 }, { 0.5, 0.5, 0.0 }, { 0.5, 0.0, 0.5 }, { 0.0, 0.5, 0.5 } };
+        int id_offset = 0;
+        N = 0;
+        for ( int rk = 0; rk < nr; rk++ )
+        {
+            Rank &r = ranks[rk];
+            r.dom = make_domain( glo, ghi, nr, rk, p.ghost_cutoff );
+            int is[3], ie[3];
+            for ( int d = 0; d < 3; d++ )
+            {
+                is[d] = (int)( r.dom.llo[d] / a - 0.5 );
+                ie[d] = (int)std::max( std::min( ghi[d] / a, r.dom.lhi[d] / a + 0.5 ),
+                                       (double)is[d] );
+                if ( is[d] == ie[d] )
+                    ie[d] -= 1;
+            }
+            std::vector<double> xs;
+            for ( int iz = is[2]; iz <= ie[2]; iz++ )
+                for ( int iy = is[1]; iy <= ie[1]; iy++ )
+                    for ( int ix = is[0]; ix <= ie[0]; ix++ )
+                        for ( int k = 0; k < 4; k++ )
+                        {
+                            double xt = a * ( 1.0 * ix + basis[k][0] );
+                            double yt = a * ( 1.0 * iy + basis[k][1] );
+                            double zt = a * ( 1.0 * iz + basis[k][2] );
+                            if ( xt >= r.dom.llo[0] && yt >= r.dom.llo[1] && zt >= r.dom.llo[2] &&
+                                 xt < r.dom.lhi[0] && yt < r.dom.lhi[1] && zt < r.dom.lhi[2] &&
+                                 xt < ghi[0] && yt < ghi[1] && zt < ghi[2] )
+                            {
+                                // in_region(): inputFile.h:183-192
+                                if ( xt >= a * blo[0] && yt >= a * blo[1] && zt >= a * blo[2] &&
+                                     xt < a * bhi[0] && yt < a * bhi[1] && zt < a * bhi[2] )
+                                {
+                                    xs.push_back( xt );
+                                    xs.push_back( yt );
+                                    xs.push_back( zt );
+                                }
+                            }
+                        }
+            int n = (int)( xs.size() / 3 );
+            r.resize( n );
+            r.N_local = n;
+            r.N_ghost = 0;
+            std::copy( xs.begin(), xs.end(), r.x.begin() );
+            std::fill( r.f.begin(), r.f.end(), 0.0 );
+            for ( int i = 0; i < n; i++ )
+            {
+                r.type[i] = 0;
+                r.id[i] = i + 1 + id_offset; // MPI_Scan offset, :778-784
+                r.q[i] = 0.0;
+            }
+            id_offset += n;
+            N += n;
+        }
+        // velocities  :811-865
+        double tm = 0, px = 0, py = 0, pz = 0;
+        for ( auto &r : ranks )
+            for ( int i = 0; i < r.N_local; i++ )
+            {
+                RandomVelocityGeom rng;
+                rng.reset( seed, &r.x[3 * i] );
+                double m = p.mass[r.type[i]];
+                double vx = rng.uniform() - 0.5;
+                double vy = rng.uniform() - 0.5;
+                double vz = rng.uniform() - 0.5;
+                r.v[3 * i] = vx / std::sqrt( m );
+                r.v[3 * i + 1] = vy / std::sqrt( m );
+                r.v[3 * i + 2] = vz / std::sqrt( m );
+                tm += m;
+                px += m * r.v[3 * i];
+                py += m * r.v[3 * i + 1];
+                pz += m * r.v[3 * i + 2];
+            }
+        const double sx = px / tm, sy = py / tm, sz = pz / tm;
+        for ( auto &r : ranks )
+            for ( int i = 0; i < r.N_local; i++ )
+            {
+                r.v[3 * i] -= sx;
+                r.v[3 * i + 1] -= sy;
+                r.v[3 * i + 2] -= sz;
+            }
+        const double T = temperature();
+        const double sc = std::sqrt( temp / T );
+        for ( auto &r : ranks )
+            for ( int i = 0; i < r.N_local; i++ )
+                for ( int d = 0; d < 3; d++ )
+                    r.v[3 * i + d] *= sc;
+    }
+
+    // property_temperature_impl.h:55-77
+    double temperature() const
+    {
+        double s = 0;
+        for ( auto &r : ranks )
+            s += sum_mv2( r, p );
+        const int dof = 3 * N - 3;
+        return s * ( p.mvv2e / ( 1.0 * dof * p.boltz ) );
+    }
+    // property_kine_impl.h:55-76 (total, not per atom)
+    double kinetic() const
+    {
+        double s = 0;
+        for ( auto &r : ranks )
+            s += sum_mv2( r, p );
+        return s * 0.5 * p.mvv2e;
+    }
+    // property_pote_impl.h:55-63 (total)
+    double potential( bool corrected = false ) const
+    {
+        double s = 0;
+        for ( auto &r : ranks )
+            s += energy( r.x.data(), r.type.data(), r.N_local, r.list, p, p.half, corrected );
+        return s;
+    }
+
+    // comm_mpi_impl.h:191-278 + comm_mpi.h:141-237 + [Cabana] Distributor/migrate:
+    // result = stayers first (original order) then imports.
+    int exchange()
+    {
+        int total_sent = 0;
+        for ( auto &r : ranks )
+        {
+            r.resize( r.N_local );
+            r.N_ghost = 0;
+            // TagExchangeSelf: wrap in dims with one rank (assumes box origin 0)
+            for ( int i = 0; i < r.N_local; i++ )
+                for ( int d = 0; d < 3; d++ )
+                    if ( r.dom.grid[d] == 1 )
+                    {
+                        const double x1 = r.x[3 * i + d];
+                        if ( x1 > r.dom.gext[d] )
+                            r.x[3 * i + d] -= r.dom.gext[d];
+                        if ( x1 < 0 )
+                            r.x[3 * i + d] += r.dom.gext[d];
+                    }
+        }
+        for ( int ph = 0; ph < 6; ph++ )
+        {
+            const int d = ph / 2;
+            if ( ranks[0].dom.grid[d] <= 1 )
+                continue;
+            std::vector<Rank> out( ranks.size() ); // outgoing tuples per source rank
+            for ( size_t rk = 0; rk < ranks.size(); rk++ )
+            {
+                Rank &r = ranks[rk];
+                Rank keep;
+                const int n = r.size();
+                auto push = []( Rank &dst, const Rank &src, int i )
+                {
+                    for ( int k = 0; k < 3; k++ )
+                    {
+                        dst.x.push_back( src.x[3 * i + k] );
+                        dst.v.push_back( src.v[3 * i + k] );
+                        dst.f.push_back( src.f[3 * i + k] );
+                    }
+                    dst.q.push_back( src.q[i] );
+                    dst.type.push_back( src.type[i] );
+                    dst.id.push_back( src.id[i] );
+                };
+                for ( int i = 0; i < n; i++ )
+                {
+                    bool go = ( ph % 2 == 0 ) ? ( r.x[3 * i + d] > r.dom.lhi[d] )
+                                              : ( r.x[3 * i + d] < r.dom.llo[d] );
+                    if ( go )
+                    {
+                        if ( ph % 2 == 0 && r.dom.pos[d] == r.dom.grid[d] - 1 )
+                            r.x[3 * i + d] -= r.dom.gext[d];
+                        if ( ph % 2 == 1 && r.dom.pos[d] == 0 )
+                            r.x[3 * i + d] += r.dom.gext[d];
+                        push( out[rk], r, i );
+                        total_sent++;
+                    }
+                    else
+                        push( keep, r, i );
+                }
+                keep.dom = r.dom;
+                std::memcpy( keep.nbr_send, r.nbr_send, sizeof( r.nbr_send ) );
+                std::memcpy( keep.nbr_recv, r.nbr_recv, sizeof( r.nbr_recv ) );
+                r = std::move( keep );
+            }
+            for ( size_t rk = 0; rk < ranks.size(); rk++ )
+            {
+                Rank &dst = ranks[ranks[rk].nbr_send[ph]];
+                Rank &o = out[rk];
+                dst.x.insert( dst.x.end(), o.x.begin(), o.x.end() );
+                dst.v.insert( dst.v.end(), o.v.begin(), o.v.end() );
+                dst.f.insert( dst.f.end(), o.f.begin(), o.f.end() );
+                dst.q.insert( dst.q.end(), o.q.begin(), o.q.end() );
+                dst.type.insert( dst.type.end(), o.type.begin(), o.type.end() );
+                dst.id.insert( dst.id.end(), o.id.begin(), o.id.end() );
+            }
+        }
+        for ( auto &r : ranks )
+        {
+            r.N_local = r.size();
+            r.N_ghost = 0;
+        }
+        return total_sent;
+    }
+
+    // comm_mpi_impl.h:280-367 + comm_mpi.h:240-353.  Ghosts receive x, type and
+    // (extension, documented) id; v/f/q of ghosts are never communicated.
+    void exchange_halo()
+    {
+        const double depth = p.neigh_cut();
+        for ( auto &r : ranks )
+            r.N_ghost = 0;
+        for ( int ph = 0; ph < 6; ph++ )
+        {
+            const int d = ph / 2;
+            for ( auto &r : ranks )
+            {
+                const int np =
+                    r.N_local + r.N_ghost - ( ( ph % 2 == 1 ) ? r.num_recv[ph - 1] : 0 );
+                r.send_idx[ph].clear();
+                for ( int i = 0; i < np; i++ )
+                {
+                    const double xv = r.x[3 * i + d];
+                    bool s = ( ph % 2 == 0 ) ? ( xv >= r.dom.lhi[d] - depth )
+                                             : ( xv <= r.dom.llo[d] + depth );
+                    if ( s )
+                        r.send_idx[ph].push_back( i );
+                }
+                r.num_send[ph] = (int)r.send_idx[ph].size();
+            }
+            // all sends are computed from pre-phase state; now deliver
+            std::vector<int> base( ranks.size() );
+            for ( size_t rk = 0; rk < ranks.size(); rk++ )
+            {
+                Rank &dst = ranks[rk];
+                const Rank &src = ranks[dst.nbr_recv[ph]];
+                base[rk] = dst.N_local + dst.N_ghost;
+                dst.num_recv[ph] = src.num_send[ph];
+            }
+            std::vector<std::vector<double>> bx( ranks.size() );
+            std::vector<std::vector<int>> bt( ranks.size() ), bi( ranks.size() );
+            for ( size_t rk = 0; rk < ranks.size(); rk++ )
+            {
+                const Rank &src = ranks[ranks[rk].nbr_recv[ph]];
+                for ( int s : src.send_idx[ph] )
+                {
+                    bx[rk].push_back( src.x[3 * s] );
+                    bx[rk].push_back( src.x[3 * s + 1] );
+                    bx[rk].push_back( src.x[3 * s + 2] );
+                    bt[rk].push_back( src.type[s] );
+                    bi[rk].push_back( src.id[s] );
+                }
+            }
+            for ( size_t rk = 0; rk < ranks.size(); rk++ )
+            {
+                Rank &dst = ranks[rk];
+                const int n0 = base[rk], nr = dst.num_recv[ph];
+                dst.resize( n0 + nr );
+                for ( int k = 0; k < nr; k++ )
+                {
+                    for ( int c = 0; c < 3; c++ )
+                    {
+                        dst.x[3 * ( n0 + k ) + c] = bx[rk][3 * k + c];
+                        dst.v[3 * ( n0 + k ) + c] = 0.0;
+                        dst.f[3 * ( n0 + k ) + c] = 0.0;
+                    }
+                    dst.type[n0 + k] = bt[rk][k];
+                    dst.id[n0 + k] = bi[rk][k];
+                    dst.q[n0 + k] = 0.0;
+                }
+                pbc_shift( dst, ph, n0, n0 + nr );
+                dst.N_ghost += nr;
+            }
+        }
+    }
+
+    // TagHaloPBC, comm_mpi.h:323-353
+    static void pbc_shift( Rank &r, int ph, int b, int e )
+    {
+        const int d = ph / 2;
+        double s = 0.0;
+        if ( ph % 2 == 0 && r.dom.pos[d] == 0 )
+            s = -r.dom.gext[d];
+        if ( ph % 2 == 1 && r.dom.pos[d] == r.dom.grid[d] - 1 )
+            s = r.dom.gext[d];
+        if ( s != 0.0 )
+            for ( int i = b; i < e; i++ )
+                r.x[3 * i + d] += s;
+    }
+
+    // comm_mpi_impl.h:369-408: replay stored plans, x only, phases sequential
+    void update_halo()
+    {
+        std::vector<int> ng( ranks.size(), 0 );
+        for ( int ph = 0; ph < 6; ph++ )
+        {
+            std::vector<std::vector<double>> bx( ranks.size() );
+            for ( size_t rk = 0; rk < ranks.size(); rk++ )
+            {
+                const Rank &src = ranks[ranks[rk].nbr_recv[ph]];
+                for ( int s : src.send_idx[ph] )
+                    for ( int c = 0; c < 3; c++ )
+                        bx[rk].push_back( src.x[3 * s + c] );
+            }
+            for ( size_t rk = 0; rk < ranks.size(); rk++ )
+            {
+                Rank &dst = ranks[rk];
+                const int n0 = dst.N_local + ng[rk], nr = dst.num_recv[ph];
+                std::copy( bx[rk].begin(), bx[rk].end(), dst.x.begin() + 3 * (size_t)n0 );
+                pbc_shift( dst, ph, n0, n0 + nr );
+                ng[rk] += nr;
+            }
+        }
+    }
+
+    // comm_mpi_impl.h:410-441: phases 5..0, ghost f added into the owner
+    void update_force()
+    {
+        std::vector<int> off( ranks.size() );
+        for ( size_t rk = 0; rk < ranks.size(); rk++ )
+            off[rk] = ranks[rk].N_local + ranks[rk].N_ghost;
+        for ( int ph = 5; ph >= 0; ph-- )
+        {
+            for ( size_t rk = 0; rk < ranks.size(); rk++ )
+                off[rk] -= ranks[rk].num_recv[ph];
+            // receiver rk's segment [off, off+num_recv) goes back to its source
+            for ( size_t rk = 0; rk < ranks.size(); rk++ )
+            {
+                const Rank &gh = ranks[rk];
+                Rank &own = ranks[gh.nbr_recv[ph]];
+                for ( int k = 0; k < gh.num_recv[ph]; k++ )
+                {
+                    const int s = own.send_idx[ph][k];
+                    for ( int c = 0; c < 3; c++ )
+                        own.f[3 * s + c] += gh.f[3 * ( off[rk] + k ) + c];
+                }
+            }
+        }
+    }
+
+    void neighbor_create()
+    {
+        for ( auto &r : ranks )
+            neigh_build( r.x.data(), r.N_local, r.N_local + r.N_ghost, p.neigh_cut(), p.half,
+                         r.dom.ghost_lo, r.dom.ghost_hi, r.list );
+    }
+
+    void force_compute()
+    {
+        for ( auto &r : ranks )
+        {
+            std::fill( r.f.begin(), r.f.end(), 0.0 ); // cabanamd_impl.h:336-338
+            if ( p.half )
+                force_half( r.x.data(), r.type.data(), r.f.data(), r.N_local, r.list, p );
+            else
+                force_full( r.x.data(), r.type.data(), r.f.data(), r.N_local, r.list, p );
+        }
+        if ( p.half )
+            update_force(); // cabanamd_impl.h:348-353
+    }
+
+    static double now()
+    {
+#ifdef _OPENMP
+        return omp_get_wtime();
+#else
+        return 0.0;
+#endif
+    }
+
+    void record_thermo()
+    {
+        thermo.push_back( { step, temperature(), potential() / N, kinetic() / N } );
+    }
+
+    // cabanamd_impl.h:197-243
+    void setup()
+    {
+        create_domain_decomposition();
+        exchange();
+        for ( auto &r : ranks )
+            create_binning( r, p.neigh_cut(), p.neigh_cut(), p.neigh_cut(), 1 );
+        exchange_halo();
+        neighbor_create();
+        force_compute();
+        step = 0;
+    }
+
+    // cabanamd_impl.h:285-399
+    void run( int nsteps, int thermo_rate )
+    {
+        for ( int s = 0; s < nsteps; s++ )
+        {
+            step++;
+            double t0 = now();
+            for ( auto &r : ranks )
+                initial_integrate( r, p );
+            double t1 = now();
+            t_int += t1 - t0;
+            if ( step % p.exchange_rate == 0 )
+            {
+                exchange();
+                double t2 = now();
+                t_comm += t2 - t1;
+                for ( auto &r : ranks )
+                    create_binning( r, p.neigh_cut(), p.neigh_cut(), p.neigh_cut(), 1 );
+                double t3 = now();
+                t_other += t3 - t2;
+                exchange_halo();
+                double t4 = now();
+                t_comm += t4 - t3;
+                neighbor_create();
+                t_neigh += now() - t4;
+            }
+            else
+            {
+                update_halo();
+                t_comm += now() - t1;
+            }
+            double t5 = now();
+            force_compute();
+            double t6 = now();
+            t_force += t6 - t5;
+            for ( auto &r : ranks )
+                final_integrate( r, p );
+            t_int += now() - t6;
+            if ( thermo_rate > 0 && step % thermo_rate == 0 )
+            {
+                double t7 = now();
+                record_thermo();
+                t_other += now() - t7;
+            }
+        }
+    }
+};
+
+} // namespace orc
