@@ -1,0 +1,803 @@
+// cbmd_comm.cu — spatial-decomposition exchange: PBC wrap / migration of owned atoms,
+// 6-phase ghost build, per-step ghost refresh and reverse force accumulation.
+// Replaces Comm<t_System> (reference src/comm_mpi.h:125-353, src/comm_mpi_impl.h:52-441)
+// and the [Cabana] Distributor/migrate + Halo/gather/scatter it delegates to.  MPI is
+// replaced by NCCL send/recv groups (one process per GPU); a phase whose face
+// neighbour is this rank itself (one rank in that dimension) is a local copy.
+//
+// The six phases (+x,-x,+y,-y,+z,-z) are kept exactly — including forwarding of
+// earlier-phase ghosts and the odd-phase exclusion of the ghosts just received
+// (comm_mpi_impl.h:301-303) — so the ghost SET equals the reference's.  Send lists
+// are produced by an ordered (ascending index) stream compaction, so ghost order is
+// deterministic, unlike the reference's atomic-append order.  When every face
+// neighbour is this rank (single GPU) each ghost also records its root owner and
+// accumulated image so update_halo is ONE gather kernel instead of six dependent
+// phases; each coordinate is shifted at most once, so the values are bit-identical.
+#include "cbmd_internal.cuh"
+
+__global__ void k_fill3( double *__restrict__ soa, int cap, int first, int n, double val );
+
+static int rank_of_pos( const int grid[3], int i, int j, int k )
+{
+    i = ( i % grid[0] + grid[0] ) % grid[0];
+    j = ( j % grid[1] + grid[1] ) % grid[1];
+    k = ( k % grid[2] + grid[2] ) % grid[2];
+    return ( i * grid[1] + j ) * grid[2] + k; // MPI_Cart order: last dimension fastest
+}
+
+// ---------------------------------------------------------------------------
+// ordered stream compaction of indices i in [0,n) with coordinate test in dim d:
+//   mode 0: x_d >= thr   mode 1: x_d <= thr   mode 2: x_d > thr   mode 3: x_d < thr
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool face_test( const XT &r, int d, int mode, double thr )
+{
+    const double c = d == 0 ? r.x : ( d == 1 ? r.y : r.z );
+    switch ( mode )
+    {
+    case 0:
+        return c >= thr;
+    case 1:
+        return c <= thr;
+    case 2:
+        return c > thr;
+    default:
+        return c < thr;
+    }
+}
+
+__global__ void __launch_bounds__( 256 )
+    k_face_flags( const XT *__restrict__ xt, int n, int d, int mode, double thr,
+                  int *__restrict__ flags )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i < n )
+        flags[i] = face_test( xt[i], d, mode, thr ) ? 1 : 0;
+    if ( i == n )
+        flags[n] = 0;
+}
+
+__global__ void __launch_bounds__( 256 )
+    k_select_scatter( const XT *__restrict__ xt, int n, int d, int mode, double thr,
+                      const int *__restrict__ pos, int *__restrict__ out, int out_cap )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    if ( face_test( xt[i], d, mode, thr ) )
+    {
+        const int p = pos[i];
+        if ( p < out_cap )
+            out[p] = i;
+    }
+}
+
+// returns the number of selected indices; pos (device, n+1 ints) holds the exclusive scan
+static int select_face( cbmd_ctx *ctx, int n, int d, int mode, double thr, int **pos_out )
+{
+    int *pos = (int *)cbmd_scratch( ctx, (size_t)( n + 1 ) * sizeof( int ) );
+    cudaStream_t s = ctx->stream;
+    k_face_flags<<<div_up( n + 1, 256 ), 256, 0, s>>>( ctx->xt, n, d, mode, thr, pos );
+    CBMD_LAUNCH_CHECK( ctx );
+    cbmd_exclusive_scan_int( ctx, pos, n );
+    CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i, pos + n, sizeof( int ), cudaMemcpyDeviceToHost,
+                                s ) );
+    CBMD_CUDA( cudaStreamSynchronize( s ) );
+    *pos_out = pos;
+    return ctx->h_pinned_i[0];
+}
+
+// ---------------------------------------------------------------------------
+// Comm::exchange — TagExchangeSelf (comm_mpi.h:141-168)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__( 256 )
+    k_exchange_self( XT *__restrict__ xt, int n, double Lx, double Ly, double Lz, int wx, int wy,
+                     int wz )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    XT r = xt[i];
+    bool ch = false;
+    if ( wx )
+    {
+        const double c = r.x;
+        if ( c > Lx )
+        {
+            r.x -= Lx;
+            ch = true;
+        }
+        if ( c < 0 )
+        {
+            r.x += Lx;
+            ch = true;
+        }
+    }
+    if ( wy )
+    {
+        const double c = r.y;
+        if ( c > Ly )
+        {
+            r.y -= Ly;
+            ch = true;
+        }
+        if ( c < 0 )
+        {
+            r.y += Ly;
+            ch = true;
+        }
+    }
+    if ( wz )
+    {
+        const double c = r.z;
+        if ( c > Lz )
+        {
+            r.z -= Lz;
+            ch = true;
+        }
+        if ( c < 0 )
+        {
+            r.z += Lz;
+            ch = true;
+        }
+    }
+    if ( ch )
+        xt[i] = r;
+}
+
+// migration tuple: the reference's 88-byte record {x[3],v[3],f[3],type,id,q}
+struct alignas( 8 ) MigTuple
+{
+    double x[3], v[3], f[3];
+    int type, id;
+    double q;
+};
+
+// stable partition: stayers keep their order in the alt arrays, leavers are packed
+// (with the PBC shift applied on the edge rank, comm_mpi.h:171-237)
+__global__ void __launch_bounds__( 256 )
+    k_migrate_split( const XT *__restrict__ xt, const double *__restrict__ v,
+                     const double *__restrict__ f, const int *__restrict__ id,
+                     const double *__restrict__ q, int cap, int n, int d, int mode, double thr,
+                     double shift, const int *__restrict__ pos, XT *__restrict__ xt_o,
+                     double *__restrict__ v_o, double *__restrict__ f_o, int *__restrict__ id_o,
+                     double *__restrict__ q_o, MigTuple *__restrict__ out )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    XT r = xt[i];
+    const int p = pos[i];
+    if ( face_test( r, d, mode, thr ) )
+    {
+        if ( d == 0 )
+            r.x += shift;
+        else if ( d == 1 )
+            r.y += shift;
+        else
+            r.z += shift;
+        MigTuple t;
+        t.x[0] = r.x;
+        t.x[1] = r.y;
+        t.x[2] = r.z;
+        for ( int c = 0; c < 3; c++ )
+        {
+            t.v[c] = v[(size_t)c * cap + i];
+            t.f[c] = f[(size_t)c * cap + i];
+        }
+        t.type = (int)r.t;
+        t.id = id[i];
+        t.q = q[i];
+        out[p] = t;
+    }
+    else
+    {
+        const int o = i - p;
+        xt_o[o] = r;
+        for ( int c = 0; c < 3; c++ )
+        {
+            v_o[(size_t)c * cap + o] = v[(size_t)c * cap + i];
+            f_o[(size_t)c * cap + o] = f[(size_t)c * cap + i];
+        }
+        id_o[o] = id[i];
+        q_o[o] = q[i];
+    }
+}
+
+__global__ void __launch_bounds__( 256 )
+    k_migrate_unpack( const MigTuple *__restrict__ in, int n, int first, int cap,
+                      XT *__restrict__ xt, double *__restrict__ v, double *__restrict__ f,
+                      int *__restrict__ id, double *__restrict__ q )
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( k >= n )
+        return;
+    const MigTuple t = in[k];
+    XT r;
+    r.x = t.x[0];
+    r.y = t.x[1];
+    r.z = t.x[2];
+    r.t = t.type;
+    const int o = first + k;
+    xt[o] = r;
+    for ( int c = 0; c < 3; c++ )
+    {
+        v[(size_t)c * cap + o] = t.v[c];
+        f[(size_t)c * cap + o] = t.f[c];
+    }
+    id[o] = t.id;
+    q[o] = t.q;
+}
+
+static void ensure_buf( double *&buf, size_t &have, size_t bytes, cudaStream_t s )
+{
+    if ( bytes <= have )
+        return;
+    if ( buf )
+    {
+        CBMD_CUDA( cudaStreamSynchronize( s ) );
+        CBMD_CUDA( cudaFree( buf ) );
+    }
+    buf = nullptr;
+    have = bytes + bytes / 4 + ( 1 << 16 );
+    CBMD_CUDA( cudaMalloc( &buf, have ) );
+}
+
+// exchange one int with the phase peers (send to peer_send, receive from peer_recv)
+static int swap_count( cbmd_ctx *ctx, int mine, int peer_send, int peer_recv )
+{
+    int *d = ctx->d_flags + 16;
+    cudaStream_t s = ctx->stream;
+    ctx->h_pinned_i[8] = mine;
+    CBMD_CUDA( cudaMemcpyAsync( d, ctx->h_pinned_i + 8, sizeof( int ), cudaMemcpyHostToDevice, s ) );
+    CBMD_NCCL( ncclGroupStart() );
+    CBMD_NCCL( ncclSend( d, 1, ncclInt, peer_send, ctx->nccl, s ) );
+    CBMD_NCCL( ncclRecv( d + 1, 1, ncclInt, peer_recv, ctx->nccl, s ) );
+    CBMD_NCCL( ncclGroupEnd() );
+    CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i + 9, d + 1, sizeof( int ), cudaMemcpyDeviceToHost,
+                                s ) );
+    CBMD_CUDA( cudaStreamSynchronize( s ) );
+    return ctx->h_pinned_i[9];
+}
+
+static void phase_peers( const cbmd_ctx *ctx, int ph, int &peer_send, int &peer_recv )
+{
+    // comm_mpi_impl.h:87-99: send +x,-x,+y,-y,+z,-z; recv = send of the opposite phase
+    int dlt[3] = { 0, 0, 0 };
+    dlt[ph / 2] = ( ph % 2 == 0 ) ? 1 : -1;
+    peer_send = rank_of_pos( ctx->grid, ctx->pos[0] + dlt[0], ctx->pos[1] + dlt[1],
+                             ctx->pos[2] + dlt[2] );
+    peer_recv = rank_of_pos( ctx->grid, ctx->pos[0] - dlt[0], ctx->pos[1] - dlt[1],
+                             ctx->pos[2] - dlt[2] );
+}
+
+extern "C" int cbmd_exchange( cbmd_ctx *ctx, int *n_sent_global )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( ctx->have_domain, "cbmd_set_domain must be called before cbmd_exchange" );
+    cbmd_materialize_zero_force( ctx );
+    cudaStream_t s = ctx->stream;
+    // system->resize(N_local): ghosts are dropped (comm_mpi_impl.h:196-197)
+    ctx->n_ghost = 0;
+    ctx->have_halo = false;
+    ctx->nb_n = 0;
+    ctx->nb_ntot = 0;
+    int n = ctx->n_local;
+    if ( n > 0 )
+    {
+        k_exchange_self<<<div_up( n, 256 ), 256, 0, s>>>( ctx->xt, n, ctx->gext[0], ctx->gext[1],
+                                                          ctx->gext[2], ctx->grid[0] == 1,
+                                                          ctx->grid[1] == 1, ctx->grid[2] == 1 );
+        CBMD_LAUNCH_CHECK( ctx );
+    }
+    int total_sent = 0;
+    for ( int ph = 0; ph < 6 && ctx->nranks > 1; ph++ )
+    {
+        const int d = ph / 2;
+        if ( ctx->grid[d] <= 1 )
+            continue;
+        int peer_send, peer_recv;
+        phase_peers( ctx, ph, peer_send, peer_recv );
+        // strict tests (comm_mpi.h:173,185,...): x > local_hi (even) / x < local_lo (odd)
+        const int mode = ( ph % 2 == 0 ) ? 2 : 3;
+        const double thr = ( ph % 2 == 0 ) ? ctx->lhi[d] : ctx->llo[d];
+        double shift = 0.0;
+        if ( ph % 2 == 0 && ctx->pos[d] == ctx->grid[d] - 1 )
+            shift = -ctx->gext[d];
+        if ( ph % 2 == 1 && ctx->pos[d] == 0 )
+            shift = ctx->gext[d];
+        n = ctx->n_local;
+        int *pos = nullptr;
+        int n_send = 0;
+        if ( n > 0 )
+            n_send = select_face( ctx, n, d, mode, thr, &pos );
+        const int n_recv = swap_count( ctx, n_send, peer_send, peer_recv );
+        ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, (size_t)( n_send + 1 ) * sizeof( MigTuple ), s );
+        ensure_buf( ctx->recvbuf, ctx->recvbuf_bytes, (size_t)( n_recv + 1 ) * sizeof( MigTuple ), s );
+        if ( n_send > 0 )
+        {
+            // pos lives in scratch: ensure_capacity below must not run before the split
+            k_migrate_split<<<div_up( n, 256 ), 256, 0, s>>>(
+                ctx->xt, ctx->v, ctx->f, ctx->id, ctx->q, ctx->cap, n, d, mode, thr, shift, pos,
+                ctx->xt_alt, ctx->v_alt, ctx->f_alt, ctx->id_alt, ctx->q_alt,
+                (MigTuple *)ctx->sendbuf );
+            CBMD_LAUNCH_CHECK( ctx );
+            std::swap( ctx->xt, ctx->xt_alt );
+            std::swap( ctx->v, ctx->v_alt );
+            std::swap( ctx->f, ctx->f_alt );
+            std::swap( ctx->id, ctx->id_alt );
+            std::swap( ctx->q, ctx->q_alt );
+        }
+        CBMD_NCCL( ncclGroupStart() );
+        if ( n_send > 0 )
+            CBMD_NCCL( ncclSend( ctx->sendbuf, (size_t)n_send * sizeof( MigTuple ), ncclChar,
+                                 peer_send, ctx->nccl, s ) );
+        if ( n_recv > 0 )
+            CBMD_NCCL( ncclRecv( ctx->recvbuf, (size_t)n_recv * sizeof( MigTuple ), ncclChar,
+                                 peer_recv, ctx->nccl, s ) );
+        CBMD_NCCL( ncclGroupEnd() );
+        const int n_keep = n - n_send;
+        ctx->n_local = n_keep; // so a regrow copies only live rows
+        cbmd_ensure_capacity( ctx, n_keep + n_recv );
+        if ( n_recv > 0 )
+        {
+            k_migrate_unpack<<<div_up( n_recv, 256 ), 256, 0, s>>>(
+                (const MigTuple *)ctx->recvbuf, n_recv, n_keep, ctx->cap, ctx->xt, ctx->v, ctx->f,
+                ctx->id, ctx->q );
+            CBMD_LAUNCH_CHECK( ctx );
+        }
+        ctx->n_local = n_keep + n_recv;
+        total_sent += n_send;
+    }
+    if ( ctx->nranks > 1 )
+        CBMD_REQUIRE( cbmd_reduce_sum_int( ctx, &total_sent, 1 ) == 0, cbmd_last_error() );
+    if ( n_sent_global )
+        *n_sent_global = total_sent;
+    CBMD_API_END
+}
+
+// ---------------------------------------------------------------------------
+// Comm::exchange_halo
+// ---------------------------------------------------------------------------
+// local (self-neighbour) ghost creation: gather by send list, shift, record owner/image
+__global__ void __launch_bounds__( 256 )
+    k_halo_make_self( XT *__restrict__ xt, int *__restrict__ id, const int *__restrict__ send_idx,
+                      int n, int first, int n_local, int d, double shift,
+                      int *__restrict__ owner, unsigned char *__restrict__ image )
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( k >= n )
+        return;
+    const int sidx = send_idx[k];
+    XT r = ld_xt( xt + sidx );
+    unsigned char img = 0;
+    int own = sidx;
+    if ( sidx >= n_local )
+    {
+        own = owner[sidx - n_local];
+        img = image[sidx - n_local];
+    }
+    if ( shift != 0.0 )
+    {
+        if ( d == 0 )
+            r.x += shift;
+        else if ( d == 1 )
+            r.y += shift;
+        else
+            r.z += shift;
+        img |= (unsigned char)( ( shift > 0.0 ? 1u : 2u ) << ( 2 * d ) );
+    }
+    const int g = first + k;
+    xt[g] = r;
+    id[g] = id[sidx];
+    owner[g - n_local] = own;
+    image[g - n_local] = img;
+}
+
+__global__ void __launch_bounds__( 256 )
+    k_halo_pack( const XT *__restrict__ xt, const int *__restrict__ id,
+                 const int *__restrict__ send_idx, int n, XT *__restrict__ out_xt,
+                 int *__restrict__ out_id )
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( k >= n )
+        return;
+    const int sidx = send_idx[k];
+    out_xt[k] = ld_xt( xt + sidx );
+    if ( out_id )
+        out_id[k] = id[sidx];
+}
+
+// TagHaloPBC (comm_mpi.h:323-353) on a freshly received segment
+__global__ void __launch_bounds__( 256 )
+    k_halo_shift( XT *__restrict__ xt, int first, int n, int d, double shift )
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( k >= n )
+        return;
+    double *c = &xt[first + k].x + d;
+    *c += shift;
+}
+
+extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( ctx->have_domain, "cbmd_set_domain must be called before cbmd_exchange_halo" );
+    CBMD_REQUIRE( comm_depth > 0, "comm depth must be positive" );
+    cbmd_materialize_zero_force( ctx );
+    cudaStream_t s = ctx->stream;
+    ctx->comm_depth = comm_depth;
+    ctx->n_ghost = 0;
+    ctx->nb_n = 0;
+    ctx->nb_ntot = 0;
+    bool all_self = true;
+    for ( int ph = 0; ph < 6; ph++ )
+    {
+        HaloPhase &P = ctx->phase[ph];
+        const int d = ph / 2;
+        phase_peers( ctx, ph, P.peer_send, P.peer_recv );
+        const bool self = ( P.peer_send == ctx->rank );
+        all_self = all_self && self;
+        // comm_mpi_impl.h:301-303
+        const int np = ctx->n_local + ctx->n_ghost - ( ( ph % 2 == 1 ) ? ctx->phase[ph - 1].n_recv : 0 );
+        // comm_mpi.h:249,263,...: x >= hi - depth (even) / x <= lo + depth (odd)
+        const int mode = ( ph % 2 == 0 ) ? 0 : 1;
+        const double thr = ( ph % 2 == 0 ) ? ctx->lhi[d] - comm_depth : ctx->llo[d] + comm_depth;
+        int *pos = nullptr;
+        P.n_send = np > 0 ? select_face( ctx, np, d, mode, thr, &pos ) : 0;
+        if ( P.n_send > P.send_cap )
+        {
+            if ( P.send_idx )
+                CBMD_CUDA( cudaFree( P.send_idx ) );
+            P.send_cap = (int)( P.n_send * 1.1 ) + 256; // comm_mpi_impl.h:313 growth policy
+            CBMD_CUDA( cudaMalloc( &P.send_idx, (size_t)P.send_cap * sizeof( int ) ) );
+        }
+        if ( P.n_send > 0 )
+        {
+            k_select_scatter<<<div_up( np, 256 ), 256, 0, s>>>( ctx->xt, np, d, mode, thr, pos,
+                                                                P.send_idx, P.send_cap );
+            CBMD_LAUNCH_CHECK( ctx );
+        }
+        // receiver-side PBC shift (TagHaloPBC)
+        P.shift = 0.0;
+        if ( ph % 2 == 0 && ctx->pos[d] == 0 )
+            P.shift = -ctx->gext[d];
+        if ( ph % 2 == 1 && ctx->pos[d] == ctx->grid[d] - 1 )
+            P.shift = ctx->gext[d];
+        const int first = ctx->n_local + ctx->n_ghost;
+        P.recv_first = first;
+        if ( self )
+        {
+            P.n_recv = P.n_send;
+            cbmd_ensure_capacity( ctx, first + P.n_recv );
+            if ( P.n_recv > 0 )
+            {
+                k_halo_make_self<<<div_up( P.n_recv, 256 ), 256, 0, s>>>(
+                    ctx->xt, ctx->id, P.send_idx, P.n_recv, first, ctx->n_local, d, P.shift,
+                    ctx->ghost_owner, ctx->ghost_image );
+                CBMD_LAUNCH_CHECK( ctx );
+            }
+        }
+        else
+        {
+            P.n_recv = swap_count( ctx, P.n_send, P.peer_send, P.peer_recv );
+            ctx->n_ghost += 0;
+            cbmd_ensure_capacity( ctx, first + P.n_recv );
+            const size_t sb = (size_t)( P.n_send + 1 ) * ( sizeof( XT ) + sizeof( int ) ) + 64;
+            ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, sb, s );
+            XT *sx = (XT *)ctx->sendbuf;
+            int *si = (int *)( sx + P.n_send + 1 );
+            if ( P.n_send > 0 )
+            {
+                k_halo_pack<<<div_up( P.n_send, 256 ), 256, 0, s>>>( ctx->xt, ctx->id, P.send_idx,
+                                                                     P.n_send, sx, si );
+                CBMD_LAUNCH_CHECK( ctx );
+            }
+            CBMD_NCCL( ncclGroupStart() );
+            if ( P.n_send > 0 )
+            {
+                CBMD_NCCL( ncclSend( sx, (size_t)P.n_send * sizeof( XT ), ncclChar, P.peer_send,
+                                     ctx->nccl, s ) );
+                CBMD_NCCL( ncclSend( si, P.n_send, ncclInt, P.peer_send, ctx->nccl, s ) );
+            }
+            if ( P.n_recv > 0 )
+            {
+                // straight into the tail: ghosts of one phase are contiguous
+                CBMD_NCCL( ncclRecv( ctx->xt + first, (size_t)P.n_recv * sizeof( XT ), ncclChar,
+                                     P.peer_recv, ctx->nccl, s ) );
+                CBMD_NCCL( ncclRecv( ctx->id + first, P.n_recv, ncclInt, P.peer_recv, ctx->nccl, s ) );
+            }
+            CBMD_NCCL( ncclGroupEnd() );
+            if ( P.n_recv > 0 && P.shift != 0.0 )
+            {
+                k_halo_shift<<<div_up( P.n_recv, 256 ), 256, 0, s>>>( ctx->xt, first, P.n_recv, d,
+                                                                      P.shift );
+                CBMD_LAUNCH_CHECK( ctx );
+            }
+        }
+        ctx->n_ghost += P.n_recv;
+    }
+    // ghost v / f are never communicated (comm_mpi_impl.h:346-347); keep them defined
+    if ( ctx->n_ghost > 0 )
+    {
+        k_fill3<<<div_up( ctx->n_ghost, 256 ), 256, 0, s>>>( ctx->v, ctx->cap, ctx->n_local,
+                                                             ctx->n_ghost, 0.0 );
+        CBMD_LAUNCH_CHECK( ctx );
+        k_fill3<<<div_up( ctx->n_ghost, 256 ), 256, 0, s>>>( ctx->f, ctx->cap, ctx->n_local,
+                                                             ctx->n_ghost, 0.0 );
+        CBMD_LAUNCH_CHECK( ctx );
+    }
+    ctx->flat_halo_ok = all_self;
+    ctx->have_halo = true;
+    CBMD_API_END
+}
+
+// ---------------------------------------------------------------------------
+// Comm::update_halo
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__( 256 )
+    k_halo_update_flat( XT *__restrict__ xt, int n_local, int n_ghost,
+                        const int *__restrict__ owner, const unsigned char *__restrict__ image,
+                        double Lx, double Ly, double Lz )
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( g >= n_ghost )
+        return;
+    XT r = ld_xt( xt + owner[g] );
+    const unsigned img = image[g];
+    const unsigned ix = img & 3u, iy = ( img >> 2 ) & 3u, iz = ( img >> 4 ) & 3u;
+    if ( ix )
+        r.x += ( ix == 1u ? Lx : -Lx );
+    if ( iy )
+        r.y += ( iy == 1u ? Ly : -Ly );
+    if ( iz )
+        r.z += ( iz == 1u ? Lz : -Lz );
+    xt[n_local + g] = r;
+}
+
+__global__ void __launch_bounds__( 256 )
+    k_halo_update_self( XT *__restrict__ xt, const int *__restrict__ send_idx, int n, int first,
+                        int d, double shift )
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( k >= n )
+        return;
+    XT r = ld_xt( xt + send_idx[k] );
+    if ( d == 0 )
+        r.x += shift;
+    else if ( d == 1 )
+        r.y += shift;
+    else
+        r.z += shift;
+    xt[first + k] = r;
+}
+
+extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( ctx->have_halo, "cbmd_exchange_halo must be called before cbmd_update_halo" );
+    cudaStream_t s = ctx->stream;
+    if ( ctx->n_ghost == 0 )
+        return 0;
+    if ( ctx->flat_halo_ok )
+    {
+        k_halo_update_flat<<<div_up( ctx->n_ghost, 256 ), 256, 0, s>>>(
+            ctx->xt, ctx->n_local, ctx->n_ghost, ctx->ghost_owner, ctx->ghost_image, ctx->gext[0],
+            ctx->gext[1], ctx->gext[2] );
+        CBMD_LAUNCH_CHECK( ctx );
+        return 0;
+    }
+    for ( int ph = 0; ph < 6; ph++ )
+    {
+        HaloPhase &P = ctx->phase[ph];
+        const int d = ph / 2;
+        if ( P.peer_send == ctx->rank )
+        {
+            if ( P.n_recv > 0 )
+            {
+                k_halo_update_self<<<div_up( P.n_recv, 256 ), 256, 0, s>>>(
+                    ctx->xt, P.send_idx, P.n_recv, P.recv_first, d, P.shift );
+                CBMD_LAUNCH_CHECK( ctx );
+            }
+            continue;
+        }
+        ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, (size_t)( P.n_send + 1 ) * sizeof( XT ), s );
+        XT *sx = (XT *)ctx->sendbuf;
+        if ( P.n_send > 0 )
+        {
+            k_halo_pack<<<div_up( P.n_send, 256 ), 256, 0, s>>>( ctx->xt, ctx->id, P.send_idx,
+                                                                 P.n_send, sx, nullptr );
+            CBMD_LAUNCH_CHECK( ctx );
+        }
+        CBMD_NCCL( ncclGroupStart() );
+        if ( P.n_send > 0 )
+            CBMD_NCCL( ncclSend( sx, (size_t)P.n_send * sizeof( XT ), ncclChar, P.peer_send,
+                                 ctx->nccl, s ) );
+        if ( P.n_recv > 0 )
+            CBMD_NCCL( ncclRecv( ctx->xt + P.recv_first, (size_t)P.n_recv * sizeof( XT ), ncclChar,
+                                 P.peer_recv, ctx->nccl, s ) );
+        CBMD_NCCL( ncclGroupEnd() );
+        if ( P.n_recv > 0 && P.shift != 0.0 )
+        {
+            k_halo_shift<<<div_up( P.n_recv, 256 ), 256, 0, s>>>( ctx->xt, P.recv_first, P.n_recv,
+                                                                  d, P.shift );
+            CBMD_LAUNCH_CHECK( ctx );
+        }
+    }
+    CBMD_API_END
+}
+
+// ---------------------------------------------------------------------------
+// Comm::update_force — phases 5..0; within a phase every send index is unique, so
+// the owner-side accumulation needs no atomics and is deterministic.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__( 256 )
+    k_force_fold( double *f, int cap, const int *__restrict__ send_idx, int n,
+                  const double *src, int src_stride, int src_first )
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( k >= n )
+        return;
+    const int o = send_idx[k];
+#pragma unroll
+    for ( int c = 0; c < 3; c++ )
+        f[(size_t)c * cap + o] += src[(size_t)c * src_stride + src_first + k];
+}
+
+extern "C" int cbmd_update_force( cbmd_ctx *ctx )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( ctx->have_halo, "cbmd_exchange_halo must be called before cbmd_update_force" );
+    cbmd_materialize_zero_force( ctx );
+    cudaStream_t s = ctx->stream;
+    for ( int ph = 5; ph >= 0; ph-- )
+    {
+        HaloPhase &P = ctx->phase[ph];
+        if ( P.peer_send == ctx->rank )
+        {
+            if ( P.n_recv > 0 )
+            {
+                k_force_fold<<<div_up( P.n_recv, 256 ), 256, 0, s>>>(
+                    ctx->f, ctx->cap, P.send_idx, P.n_recv, ctx->f, ctx->cap, P.recv_first );
+                CBMD_LAUNCH_CHECK( ctx );
+            }
+            continue;
+        }
+        // ghosts I received in this phase go back to peer_recv; what I sent comes back from peer_send
+        ensure_buf( ctx->recvbuf, ctx->recvbuf_bytes, 3 * (size_t)( P.n_send + 1 ) * sizeof( double ), s );
+        CBMD_NCCL( ncclGroupStart() );
+        for ( int c = 0; c < 3; c++ )
+        {
+            if ( P.n_recv > 0 )
+                CBMD_NCCL( ncclSend( ctx->f + (size_t)c * ctx->cap + P.recv_first, P.n_recv,
+                                     ncclDouble, P.peer_recv, ctx->nccl, s ) );
+            if ( P.n_send > 0 )
+                CBMD_NCCL( ncclRecv( ctx->recvbuf + (size_t)c * P.n_send, P.n_send, ncclDouble,
+                                     P.peer_send, ctx->nccl, s ) );
+        }
+        CBMD_NCCL( ncclGroupEnd() );
+        if ( P.n_send > 0 )
+        {
+            k_force_fold<<<div_up( P.n_send, 256 ), 256, 0, s>>>( ctx->f, ctx->cap, P.send_idx,
+                                                                  P.n_send, ctx->recvbuf, P.n_send,
+                                                                  0 );
+            CBMD_LAUNCH_CHECK( ctx );
+        }
+    }
+    CBMD_API_END
+}
+
+// ---------------------------------------------------------------------------
+// communicator + scalar collectives (comm_mpi_impl.h:52-76,121-189)
+// ---------------------------------------------------------------------------
+extern "C" int cbmd_comm_unique_id( void *id128 )
+{
+    try
+    {
+        static_assert( sizeof( ncclUniqueId ) == 128, "ncclUniqueId size" );
+        ncclUniqueId id;
+        CBMD_NCCL( ncclGetUniqueId( &id ) );
+        memcpy( id128, &id, sizeof( id ) );
+        return 0;
+    }
+    catch ( const std::exception &e )
+    {
+        cbmd_set_error( e.what() );
+        return 1;
+    }
+}
+
+extern "C" int cbmd_comm_init( cbmd_ctx *ctx, int nranks, int rank, const void *id128 )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks" );
+    if ( ctx->nccl )
+    {
+        CBMD_NCCL( ncclCommDestroy( ctx->nccl ) );
+        ctx->nccl = nullptr;
+    }
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    if ( nranks > 1 )
+    {
+        CBMD_REQUIRE( id128 != nullptr, "multi-rank communicator needs the NCCL unique id" );
+        ncclUniqueId id;
+        memcpy( &id, id128, sizeof( id ) );
+        CBMD_NCCL( ncclCommInitRank( &ctx->nccl, nranks, id, rank ) );
+    }
+    CBMD_API_END
+}
+
+extern "C" int cbmd_comm_rank( cbmd_ctx *ctx, int *rank, int *nranks )
+{
+    CBMD_API_BEGIN
+    if ( rank )
+        *rank = ctx->rank;
+    if ( nranks )
+        *nranks = ctx->nranks;
+    CBMD_API_END
+}
+
+template <class T>
+static void allreduce_small( cbmd_ctx *ctx, T *vals, int count, ncclDataType_t dt, ncclRedOp_t op )
+{
+    if ( ctx->nranks == 1 || count == 0 )
+        return;
+    CBMD_REQUIRE( count * sizeof( T ) <= 1024, "scalar reductions are limited to 1 KiB" );
+    cudaStream_t s = ctx->stream;
+    void *d = (void *)( ctx->d_red + 40000 );
+    CBMD_CUDA( cudaMemcpyAsync( d, vals, count * sizeof( T ), cudaMemcpyHostToDevice, s ) );
+    CBMD_NCCL( ncclAllReduce( d, d, count, dt, op, ctx->nccl, s ) );
+    CBMD_CUDA( cudaMemcpyAsync( vals, d, count * sizeof( T ), cudaMemcpyDeviceToHost, s ) );
+    CBMD_CUDA( cudaStreamSynchronize( s ) );
+}
+
+extern "C" int cbmd_reduce_sum_double( cbmd_ctx *ctx, double *vals, int count )
+{
+    CBMD_API_BEGIN
+    allreduce_small( ctx, vals, count, ncclDouble, ncclSum );
+    CBMD_API_END
+}
+extern "C" int cbmd_reduce_sum_int( cbmd_ctx *ctx, int *vals, int count )
+{
+    CBMD_API_BEGIN
+    allreduce_small( ctx, vals, count, ncclInt, ncclSum );
+    CBMD_API_END
+}
+extern "C" int cbmd_reduce_max_double( cbmd_ctx *ctx, double *vals, int count )
+{
+    CBMD_API_BEGIN
+    allreduce_small( ctx, vals, count, ncclDouble, ncclMax );
+    CBMD_API_END
+}
+extern "C" int cbmd_reduce_max_int( cbmd_ctx *ctx, int *vals, int count )
+{
+    CBMD_API_BEGIN
+    allreduce_small( ctx, vals, count, ncclInt, ncclMax );
+    CBMD_API_END
+}
+// MPI_Scan (inclusive prefix sum over ranks), comm_mpi_impl.h:121-129
+extern "C" int cbmd_scan_sum_int( cbmd_ctx *ctx, int *vals, int count )
+{
+    CBMD_API_BEGIN
+    if ( ctx->nranks > 1 && count > 0 )
+    {
+        CBMD_REQUIRE( (size_t)count * ctx->nranks * sizeof( int ) <= 4096, "scan too large" );
+        cudaStream_t s = ctx->stream;
+        int *d = (int *)( ctx->d_red + 41000 );
+        CBMD_CUDA( cudaMemcpyAsync( d + (size_t)ctx->rank * count, vals, count * sizeof( int ),
+                                    cudaMemcpyHostToDevice, s ) );
+        CBMD_NCCL( ncclAllGather( d + (size_t)ctx->rank * count, d, count, ncclInt, ctx->nccl, s ) );
+        std::vector<int> all( (size_t)count * ctx->nranks );
+        CBMD_CUDA( cudaMemcpyAsync( all.data(), d, all.size() * sizeof( int ),
+                                    cudaMemcpyDeviceToHost, s ) );
+        CBMD_CUDA( cudaStreamSynchronize( s ) );
+        for ( int k = 0; k < count; k++ )
+        {
+            int acc = 0;
+            for ( int r = 0; r <= ctx->rank; r++ )
+                acc += all[(size_t)r * count + k];
+            vals[k] = acc;
+        }
+    }
+    CBMD_API_END
+}

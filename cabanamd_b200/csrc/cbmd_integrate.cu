@@ -1,0 +1,158 @@
+// cbmd_integrate.cu — NVE velocity-Verlet half steps and the thermo reductions.
+// Replaces Integrator::initial_integrate / final_integrate (reference
+// src/integrator_nve.h:91-110, src/integrator_nve_impl.h:50-83) and the sum(m v^2)
+// reductions of Temperature / KinE (src/property_temperature.h:73-79,
+// src/property_kine.h:72-78).
+//
+// Pure streaming kernels (HBM bound): initial = 32+24+24 B read, 32+24 B written
+// per atom; final = 8 (type) + 24 + 24 read, 24 written.  Products and sums are
+// kept un-contracted (__dmul_rn/__dadd_rn) so results are bit-identical to the
+// reference's host arithmetic (mul then add, two roundings).
+#include "cbmd_internal.cuh"
+
+__global__ void __launch_bounds__( 256 )
+    k_integrate_initial( XT *__restrict__ xt, double *__restrict__ v, const double *__restrict__ f,
+                         int cap, int n, const __grid_constant__ MassTable mt, double dtv )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    XT r = xt[i];
+    const double dtfm = mt.dtfm[r.t];
+    double vx = v[i], vy = v[(size_t)cap + i], vz = v[2 * (size_t)cap + i];
+    const double fx = f[i], fy = f[(size_t)cap + i], fz = f[2 * (size_t)cap + i];
+    vx = __dadd_rn( vx, __dmul_rn( dtfm, fx ) );
+    vy = __dadd_rn( vy, __dmul_rn( dtfm, fy ) );
+    vz = __dadd_rn( vz, __dmul_rn( dtfm, fz ) );
+    r.x = __dadd_rn( r.x, __dmul_rn( dtv, vx ) );
+    r.y = __dadd_rn( r.y, __dmul_rn( dtv, vy ) );
+    r.z = __dadd_rn( r.z, __dmul_rn( dtv, vz ) );
+    v[i] = vx;
+    v[(size_t)cap + i] = vy;
+    v[2 * (size_t)cap + i] = vz;
+    xt[i] = r;
+}
+
+__global__ void __launch_bounds__( 256 )
+    k_integrate_final( const XT *__restrict__ xt, double *__restrict__ v,
+                       const double *__restrict__ f, int cap, int n, const __grid_constant__ MassTable mt )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    const long long t = xt[i].t;
+    const double dtfm = mt.dtfm[t];
+    v[i] = __dadd_rn( v[i], __dmul_rn( dtfm, f[i] ) );
+    v[(size_t)cap + i] = __dadd_rn( v[(size_t)cap + i], __dmul_rn( dtfm, f[(size_t)cap + i] ) );
+    v[2 * (size_t)cap + i] =
+        __dadd_rn( v[2 * (size_t)cap + i], __dmul_rn( dtfm, f[2 * (size_t)cap + i] ) );
+}
+
+extern "C" int cbmd_integrate_initial( cbmd_ctx *ctx )
+{
+    CBMD_API_BEGIN
+    cbmd_materialize_zero_force( ctx );
+    const int n = ctx->n_local;
+    if ( n > 0 )
+    {
+        k_integrate_initial<<<div_up( n, 256 ), 256, 0, ctx->stream>>>( ctx->xt, ctx->v, ctx->f,
+                                                                     ctx->cap, n, ctx->mass,
+                                                                     ctx->dt );
+        CBMD_LAUNCH_CHECK( ctx );
+    }
+    CBMD_API_END
+}
+
+extern "C" int cbmd_integrate_final( cbmd_ctx *ctx )
+{
+    CBMD_API_BEGIN
+    cbmd_materialize_zero_force( ctx );
+    const int n = ctx->n_local;
+    if ( n > 0 )
+    {
+        k_integrate_final<<<div_up( n, 256 ), 256, 0, ctx->stream>>>( ctx->xt, ctx->v, ctx->f,
+                                                                   ctx->cap, n, ctx->mass );
+        CBMD_LAUNCH_CHECK( ctx );
+    }
+    CBMD_API_END
+}
+
+// ---------------------------------------------------------------------------
+// deterministic two-level reduction: per-block partials in a fixed grid, then one
+// block sums the partials in index order.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_256( double val, double *sh )
+{
+    for ( int o = 16; o > 0; o >>= 1 )
+        val += __shfl_down_sync( 0xffffffffu, val, o );
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if ( lane == 0 )
+        sh[w] = val;
+    __syncthreads();
+    double r = 0.0;
+    if ( w == 0 )
+    {
+        r = lane < ( blockDim.x >> 5 ) ? sh[lane] : 0.0;
+        for ( int o = 16; o > 0; o >>= 1 )
+            r += __shfl_down_sync( 0xffffffffu, r, o );
+    }
+    __syncthreads();
+    return r; // valid in thread 0
+}
+
+__global__ void __launch_bounds__( 256 )
+    k_sum_mv2( const XT *__restrict__ xt, const double *__restrict__ v, int cap, int n,
+               const __grid_constant__ MassTable mt, double *__restrict__ partial )
+{
+    __shared__ double sh[8];
+    double acc = 0.0;
+    for ( int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+    {
+        const double vx = v[i], vy = v[(size_t)cap + i], vz = v[2 * (size_t)cap + i];
+        acc += ( vx * vx + vy * vy + vz * vz ) * mt.mass[xt[i].t];
+    }
+    const double s = block_sum_256( acc, sh );
+    if ( threadIdx.x == 0 )
+        partial[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__( 256 )
+    k_final_sum( const double *__restrict__ partial, int nparts, int nvals,
+                 double *__restrict__ out )
+{
+    // out[k] = sum_b partial[k*nparts + b]
+    __shared__ double sh[8];
+    for ( int k = 0; k < nvals; k++ )
+    {
+        double acc = 0.0;
+        for ( int b = threadIdx.x; b < nparts; b += blockDim.x )
+            acc += partial[(size_t)k * nparts + b];
+        const double s = block_sum_256( acc, sh );
+        if ( threadIdx.x == 0 )
+            out[k] = s;
+    }
+}
+
+extern "C" int cbmd_sum_mv2( cbmd_ctx *ctx, double *sum )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( sum != nullptr, "null output" );
+    const int n = ctx->n_local;
+    if ( n == 0 )
+    {
+        *sum = 0.0;
+        return 0;
+    }
+    int nblk = div_up( n, 256 );
+    if ( nblk > 1184 )
+        nblk = 1184; // 148 SMs x 8 resident CTAs
+    k_sum_mv2<<<nblk, 256, 0, ctx->stream>>>( ctx->xt, ctx->v, ctx->cap, n, ctx->mass, ctx->d_red );
+    CBMD_LAUNCH_CHECK( ctx );
+    k_final_sum<<<1, 256, 0, ctx->stream>>>( ctx->d_red, nblk, 1, ctx->d_red + 32768 );
+    CBMD_LAUNCH_CHECK( ctx );
+    CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned, ctx->d_red + 32768, sizeof( double ),
+                                cudaMemcpyDeviceToHost, ctx->stream ) );
+    CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    *sum = ctx->h_pinned[0];
+    CBMD_API_END
+}

@@ -1,0 +1,251 @@
+// cbmd_internal.cuh — context, device layout and helpers shared by the kernels of
+// libcbmd_cuda.so (sm_100a only).  See DESIGN.md for the layout rationale.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/cbmd_c_api.h"
+
+// ---------------------------------------------------------------------------
+// Position record: x, y, z and the atom type in one 32-byte sector so a neighbour
+// gather is exactly one LDG.E.256 (sm_100a) and one DRAM/L2 sector.
+// ---------------------------------------------------------------------------
+struct alignas( 32 ) XT
+{
+    double x, y, z;
+    long long t; // atom type (reference: separate int slice `type`)
+};
+
+#define CBMD_MAX_TYPES 8
+
+struct LJTable
+{
+    int ntypes;
+    double lj1[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+    double lj2[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+    double cutsq[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+};
+
+struct MassTable
+{
+    double dtfm[CBMD_MAX_TYPES]; // dtf / mass[type]
+    double mass[CBMD_MAX_TYPES];
+};
+
+// one of the six halo phases (comm_mpi_impl.h:280-367)
+struct HaloPhase
+{
+    int n_send = 0, n_recv = 0;
+    int recv_first = 0;     // first ghost index of this phase's segment
+    int *send_idx = nullptr; // device, capacity send_cap
+    int send_cap = 0;
+    double shift = 0.0;     // PBC shift the RECEIVER applies in dim phase/2
+    int peer_send = -1, peer_recv = -1;
+};
+
+struct cbmd_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+
+    // units / tables
+    double boltz = 1.0, mvv2e = 1.0, dt = 0.005;
+    int ntypes = 1;
+    MassTable mass;
+    LJTable lj;
+
+    // domain (system.h:88-113)
+    double glo[3], ghi[3], gext[3], llo[3], lhi[3], ghost_lo[3], ghost_hi[3];
+    int grid[3] = { 1, 1, 1 }, pos[3] = { 0, 0, 0 };
+    bool have_domain = false;
+
+    // atoms: [0,n_local) owned, [n_local,n_local+n_ghost) ghosts
+    int n_local = 0, n_ghost = 0, cap = 0;
+    XT *xt = nullptr, *xt_alt = nullptr;
+    double *v = nullptr, *v_alt = nullptr; // SoA [3][cap]
+    double *f = nullptr, *f_alt = nullptr; // SoA [3][cap]
+    int *id = nullptr, *id_alt = nullptr;
+    double *q = nullptr, *q_alt = nullptr;
+    bool f_zero_pending = false; // deferred deep_copy(f,0): fused into the full-list force kernel
+
+    // binning grid (binning_cabana.h:62-68) + cell lists over all atoms
+    int nbin[3] = { 0, 0, 0 }, nhalo = 0;
+    int ncell[3] = { 0, 0, 0 };
+    double bmin[3], bmax[3], brdx[3];
+    bool have_bins = false;
+    int *cell_start = nullptr; // [ncells+1]
+    int *cell_cursor = nullptr;
+    int ncells_cap = 0;
+    int *cell_atoms = nullptr; // [cap] atom indices sorted by (cell, index)
+    int *atom_cell = nullptr;  // [cap]
+    int *perm = nullptr;       // [cap] last sort permutation
+    int perm_n = 0;
+
+    // Verlet list, padded + transposed: neighbour n of atom i at nb[n*nb_stride + i]
+    int nb_half = 0, nb_layout = 0;
+    int nb_rows = 0;   // row capacity (max_neigh_guess in effect)
+    int nb_stride = 0; // >= n_local, multiple of 32
+    int nb_n = 0;      // n_local at build time
+    int nb_ntot = 0;
+    int *nb = nullptr;
+    size_t nb_alloc = 0;
+    int *nb_count = nullptr; // [cap]
+    int nb_max = 0;          // max row length of the last build
+    double nb_rcut = 0.0;
+
+    // comm
+    int nranks = 1, rank = 0;
+    ncclComm_t nccl = nullptr;
+    HaloPhase phase[6];
+    double comm_depth = 0.0;
+    bool have_halo = false;
+    int *ghost_owner = nullptr;           // [cap] root owned atom of each ghost (single-rank fast path)
+    unsigned char *ghost_image = nullptr; // [cap] packed image flags
+    bool flat_halo_ok = false;
+    double *sendbuf = nullptr, *recvbuf = nullptr;
+    size_t sendbuf_bytes = 0, recvbuf_bytes = 0;
+
+    // scratch
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    double *d_red = nullptr; // small device reduction buffer
+    int *d_flags = nullptr;  // small device int buffer (counters)
+    double *h_pinned = nullptr;
+    int *h_pinned_i = nullptr;
+
+    // options
+    int force_variant = 0;
+};
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+void cbmd_set_error( const std::string &msg );
+
+struct CbmdError : std::runtime_error
+{
+    using std::runtime_error::runtime_error;
+};
+
+#define CBMD_CUDA( call )                                                                         \
+    do                                                                                            \
+    {                                                                                             \
+        cudaError_t e__ = ( call );                                                               \
+        if ( e__ != cudaSuccess )                                                                 \
+            throw CbmdError( std::string( #call ) + " failed: " + cudaGetErrorString( e__ ) +     \
+                             " (" + __FILE__ + ":" + std::to_string( __LINE__ ) + ")" );          \
+    } while ( 0 )
+
+#define CBMD_NCCL( call )                                                                         \
+    do                                                                                            \
+    {                                                                                             \
+        ncclResult_t e__ = ( call );                                                              \
+        if ( e__ != ncclSuccess )                                                                 \
+            throw CbmdError( std::string( #call ) + " failed: " + ncclGetErrorString( e__ ) +     \
+                             " (" + __FILE__ + ":" + std::to_string( __LINE__ ) + ")" );          \
+    } while ( 0 )
+
+#define CBMD_REQUIRE( cond, msg )                                                                 \
+    do                                                                                            \
+    {                                                                                             \
+        if ( !( cond ) )                                                                          \
+            throw CbmdError( std::string( msg ) + " (" + __FILE__ + ":" +                         \
+                             std::to_string( __LINE__ ) + ")" );                                  \
+    } while ( 0 )
+
+#define CBMD_API_BEGIN                                                                            \
+    try                                                                                           \
+    {                                                                                             \
+        if ( !ctx )                                                                               \
+            throw CbmdError( "null context" );                                                    \
+        CBMD_CUDA( cudaSetDevice( ctx->device ) );
+
+#define CBMD_API_END                                                                              \
+    return 0;                                                                                     \
+    }                                                                                             \
+    catch ( const std::exception &e )                                                             \
+    {                                                                                             \
+        cbmd_set_error( e.what() );                                                               \
+        return 1;                                                                                 \
+    }
+
+#define CBMD_LAUNCH_CHECK( ctx )                                                                  \
+    do                                                                                            \
+    {                                                                                             \
+        ( ctx )->launches++;                                                                      \
+        CBMD_CUDA( cudaGetLastError() );                                                          \
+    } while ( 0 )
+
+inline int div_up( int a, int b ) { return ( a + b - 1 ) / b; }
+inline int64_t div_up64( int64_t a, int64_t b ) { return ( a + b - 1 ) / b; }
+
+// internal host helpers implemented across the .cu files
+void cbmd_ensure_capacity( cbmd_ctx *ctx, int n );
+void *cbmd_scratch( cbmd_ctx *ctx, size_t bytes );
+void cbmd_materialize_zero_force( cbmd_ctx *ctx );
+void cbmd_exclusive_scan_int( cbmd_ctx *ctx, int *data, int n ); // in place, data[n] = total
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ XT ld_xt( const XT *p )
+{
+    XT r;
+    double t;
+    asm volatile( "ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                  : "=d"( r.x ), "=d"( r.y ), "=d"( r.z ), "=d"( t )
+                  : "l"( p ) );
+    r.t = __double_as_longlong( t );
+    return r;
+}
+
+// exact (un-contracted) squared distance, summed left to right: the neighbour
+// criterion must be bit-identical to the oracle's -ffp-contract=off evaluation.
+__device__ __forceinline__ double dist2_exact( double dx, double dy, double dz )
+{
+    return __dadd_rn( __dadd_rn( __dmul_rn( dx, dx ), __dmul_rn( dy, dy ) ), __dmul_rn( dz, dz ) );
+}
+
+// cell coordinate of one position component: floor((x-min)*rdx) clamped, evaluated
+// without contraction ([Cabana] LinkedCellList / oracle CellGrid::cell1).
+__device__ __forceinline__ int cell_coord( double xv, double mn, double rdx, int n )
+{
+    int c = (int)floor( __dmul_rn( __dsub_rn( xv, mn ), rdx ) );
+    c = c < 0 ? 0 : c;
+    c = c > n - 1 ? n - 1 : c;
+    return c;
+}
+
+struct GridDesc
+{
+    double mn[3], rdx[3];
+    int n[3];
+};
+
+__device__ __forceinline__ int cell_of( const GridDesc &g, double x, double y, double z )
+{
+    int a = cell_coord( x, g.mn[0], g.rdx[0], g.n[0] );
+    int b = cell_coord( y, g.mn[1], g.rdx[1], g.n[1] );
+    int c = cell_coord( z, g.mn[2], g.rdx[2], g.n[2] );
+    return ( a * g.n[1] + b ) * g.n[2] + c;
+}
+
+inline GridDesc make_grid_desc( const cbmd_ctx *ctx )
+{
+    GridDesc g;
+    for ( int d = 0; d < 3; d++ )
+    {
+        g.mn[d] = ctx->bmin[d];
+        g.rdx[d] = ctx->brdx[d];
+        g.n[d] = ctx->ncell[d];
+    }
+    return g;
+}

@@ -1,0 +1,503 @@
+// cbmd_system.cu — context life cycle, particle store and host<->device transfers.
+// Replaces System<Device,layout> (reference src/system.h:65-279,
+// src/system_types/system_1aosoa.h:19-106): the three AoSoA layouts collapse to one
+// device layout (32-byte position+type records, SoA velocities/forces).
+#include "cbmd_internal.cuh"
+
+static thread_local std::string g_last_error;
+
+void cbmd_set_error( const std::string &msg ) { g_last_error = msg; }
+
+extern "C" const char *cbmd_last_error( void ) { return g_last_error.c_str(); }
+extern "C" const char *cbmd_version( void ) { return "cabanamd_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------
+// capacity management: System::resize only grows storage (system_1aosoa.h:59-67)
+// ---------------------------------------------------------------------------
+template <class T>
+static void regrow( T *&p, size_t old_count, size_t new_count, cudaStream_t s )
+{
+    T *np = nullptr;
+    CBMD_CUDA( cudaMalloc( &np, new_count * sizeof( T ) ) );
+    if ( p && old_count )
+        CBMD_CUDA( cudaMemcpyAsync( np, p, old_count * sizeof( T ), cudaMemcpyDeviceToDevice, s ) );
+    if ( p )
+    {
+        CBMD_CUDA( cudaStreamSynchronize( s ) );
+        CBMD_CUDA( cudaFree( p ) );
+    }
+    p = np;
+}
+
+static void regrow_soa3( double *&p, int old_cap, int new_cap, int n_used, cudaStream_t s )
+{
+    double *np = nullptr;
+    CBMD_CUDA( cudaMalloc( &np, 3 * (size_t)new_cap * sizeof( double ) ) );
+    CBMD_CUDA( cudaMemsetAsync( np, 0, 3 * (size_t)new_cap * sizeof( double ), s ) );
+    if ( p && n_used )
+        for ( int c = 0; c < 3; c++ )
+            CBMD_CUDA( cudaMemcpyAsync( np + (size_t)c * new_cap, p + (size_t)c * old_cap,
+                                        (size_t)n_used * sizeof( double ),
+                                        cudaMemcpyDeviceToDevice, s ) );
+    if ( p )
+    {
+        CBMD_CUDA( cudaStreamSynchronize( s ) );
+        CBMD_CUDA( cudaFree( p ) );
+    }
+    p = np;
+}
+
+template <class T>
+static void realloc_plain( T *&p, size_t count )
+{
+    if ( p )
+        CBMD_CUDA( cudaFree( p ) );
+    p = nullptr;
+    CBMD_CUDA( cudaMalloc( &p, count * sizeof( T ) ) );
+}
+
+void cbmd_ensure_capacity( cbmd_ctx *ctx, int n )
+{
+    if ( n <= ctx->cap )
+        return;
+    int new_cap = n + n / 4 + 1024;
+    new_cap = ( new_cap + 127 ) & ~127;
+    const int used = ctx->n_local + ctx->n_ghost;
+    cudaStream_t s = ctx->stream;
+    regrow( ctx->xt, used, new_cap, s );
+    regrow_soa3( ctx->v, ctx->cap, new_cap, used, s );
+    regrow_soa3( ctx->f, ctx->cap, new_cap, used, s );
+    regrow( ctx->id, used, new_cap, s );
+    regrow( ctx->q, used, new_cap, s );
+    regrow( ctx->nb_count, used, new_cap, s );
+    regrow( ctx->ghost_owner, used, new_cap, s );
+    regrow( ctx->ghost_image, used, new_cap, s );
+    // pure scratch / derived arrays: contents need not survive
+    realloc_plain( ctx->xt_alt, new_cap );
+    realloc_plain( ctx->v_alt, 3 * (size_t)new_cap );
+    realloc_plain( ctx->f_alt, 3 * (size_t)new_cap );
+    realloc_plain( ctx->id_alt, new_cap );
+    realloc_plain( ctx->q_alt, new_cap );
+    realloc_plain( ctx->cell_atoms, new_cap );
+    realloc_plain( ctx->atom_cell, new_cap );
+    realloc_plain( ctx->perm, new_cap );
+    ctx->cap = new_cap;
+}
+
+void *cbmd_scratch( cbmd_ctx *ctx, size_t bytes )
+{
+    if ( bytes > ctx->scratch_bytes )
+    {
+        if ( ctx->scratch )
+        {
+            CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );
+            CBMD_CUDA( cudaFree( ctx->scratch ) );
+        }
+        ctx->scratch = nullptr;
+        size_t nb = bytes + bytes / 4 + ( 1 << 20 );
+        CBMD_CUDA( cudaMalloc( &ctx->scratch, nb ) );
+        ctx->scratch_bytes = nb;
+    }
+    return ctx->scratch;
+}
+
+// ---------------------------------------------------------------------------
+// pack / unpack kernels between the reference's [n][3] slices and the device layout
+// ---------------------------------------------------------------------------
+__global__ void k_pack_xt( XT *__restrict__ xt, const double *__restrict__ x3,
+                           const int *__restrict__ type, int first, int n )
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    XT r;
+    r.x = x3[3 * (size_t)i];
+    r.y = x3[3 * (size_t)i + 1];
+    r.z = x3[3 * (size_t)i + 2];
+    r.t = type ? type[i] : 0;
+    xt[first + i] = r;
+}
+
+__global__ void k_unpack_xt( const XT *__restrict__ xt, double *__restrict__ x3,
+                             int *__restrict__ type, int first, int n )
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    XT r = xt[first + i];
+    if ( x3 )
+    {
+        x3[3 * (size_t)i] = r.x;
+        x3[3 * (size_t)i + 1] = r.y;
+        x3[3 * (size_t)i + 2] = r.z;
+    }
+    if ( type )
+        type[i] = (int)r.t;
+}
+
+// aos3 [n][3]  <->  soa [3][cap]
+__global__ void k_aos_to_soa( double *__restrict__ soa, int cap, const double *__restrict__ aos,
+                              int first, int n )
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x; // flat element of aos
+    if ( k >= 3 * n )
+        return;
+    int i = k / 3, c = k - 3 * i;
+    soa[(size_t)c * cap + first + i] = aos[k];
+}
+
+__global__ void k_soa_to_aos( const double *__restrict__ soa, int cap, double *__restrict__ aos,
+                              int first, int n )
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( k >= 3 * n )
+        return;
+    int i = k / 3, c = k - 3 * i;
+    aos[k] = soa[(size_t)c * cap + first + i];
+}
+
+__global__ void k_iota( int *__restrict__ a, int first, int n, int base )
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i < n )
+        a[first + i] = base + i;
+}
+
+__global__ void k_fill3( double *__restrict__ soa, int cap, int first, int n, double val )
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    soa[first + i] = val;
+    soa[(size_t)cap + first + i] = val;
+    soa[2 * (size_t)cap + first + i] = val;
+}
+
+void cbmd_materialize_zero_force( cbmd_ctx *ctx )
+{
+    if ( !ctx->f_zero_pending )
+        return;
+    const int n = ctx->n_local + ctx->n_ghost;
+    if ( n > 0 )
+    {
+        k_fill3<<<div_up( n, 256 ), 256, 0, ctx->stream>>>( ctx->f, ctx->cap, 0, n, 0.0 );
+        CBMD_LAUNCH_CHECK( ctx );
+    }
+    ctx->f_zero_pending = false;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" int cbmd_create( cbmd_ctx **out, int device )
+{
+    try
+    {
+        if ( !out )
+            throw CbmdError( "null out pointer" );
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount( &ndev );
+        if ( e != cudaSuccess || ndev == 0 )
+            throw CbmdError( std::string( "no CUDA device available (this library has no CPU "
+                                          "fallback): " ) +
+                             cudaGetErrorString( e ) );
+        if ( device < 0 || device >= ndev )
+            throw CbmdError( "device index out of range" );
+        CBMD_CUDA( cudaSetDevice( device ) );
+        cudaDeviceProp prop;
+        CBMD_CUDA( cudaGetDeviceProperties( &prop, device ) );
+        if ( prop.major != 10 )
+            throw CbmdError( std::string( "libcbmd_cuda is built for sm_100a only; device is " ) +
+                             prop.name + " (sm_" + std::to_string( prop.major ) +
+                             std::to_string( prop.minor ) + ")" );
+        cbmd_ctx *ctx = new cbmd_ctx;
+        ctx->device = device;
+        CBMD_CUDA( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
+        memset( &ctx->mass, 0, sizeof( ctx->mass ) );
+        memset( &ctx->lj, 0, sizeof( ctx->lj ) );
+        ctx->lj.ntypes = 1;
+        for ( int t = 0; t < CBMD_MAX_TYPES; t++ )
+        {
+            ctx->mass.mass[t] = 1.0;
+            ctx->mass.dtfm[t] = 0.5 * ctx->dt / ctx->mvv2e;
+        }
+        CBMD_CUDA( cudaMalloc( &ctx->d_red, 65536 * sizeof( double ) ) );
+        CBMD_CUDA( cudaMalloc( &ctx->d_flags, 65536 * sizeof( int ) ) );
+        CBMD_CUDA( cudaMallocHost( &ctx->h_pinned, 64 * sizeof( double ) ) );
+        CBMD_CUDA( cudaMallocHost( &ctx->h_pinned_i, 64 * sizeof( int ) ) );
+        *out = ctx;
+        return 0;
+    }
+    catch ( const std::exception &e )
+    {
+        cbmd_set_error( e.what() );
+        return 1;
+    }
+}
+
+extern "C" int cbmd_destroy( cbmd_ctx *ctx )
+{
+    if ( !ctx )
+        return 0;
+    cudaSetDevice( ctx->device );
+    cudaStreamSynchronize( ctx->stream );
+    void *ptrs[] = { ctx->xt,         ctx->xt_alt,      ctx->v,          ctx->v_alt,
+                     ctx->f,          ctx->f_alt,       ctx->id,         ctx->id_alt,
+                     ctx->q,          ctx->q_alt,       ctx->cell_start, ctx->cell_cursor,
+                     ctx->cell_atoms, ctx->atom_cell,   ctx->perm,       ctx->nb,
+                     ctx->nb_count,   ctx->ghost_owner, ctx->ghost_image, ctx->sendbuf,
+                     ctx->recvbuf,    ctx->scratch,     ctx->d_red,      ctx->d_flags };
+    for ( void *p : ptrs )
+        if ( p )
+            cudaFree( p );
+    for ( int ph = 0; ph < 6; ph++ )
+        if ( ctx->phase[ph].send_idx )
+            cudaFree( ctx->phase[ph].send_idx );
+    if ( ctx->h_pinned )
+        cudaFreeHost( ctx->h_pinned );
+    if ( ctx->h_pinned_i )
+        cudaFreeHost( ctx->h_pinned_i );
+    if ( ctx->nccl )
+        ncclCommDestroy( ctx->nccl );
+    cudaStreamDestroy( ctx->stream );
+    delete ctx;
+    return 0;
+}
+
+extern "C" int cbmd_sync( cbmd_ctx *ctx )
+{
+    CBMD_API_BEGIN
+    CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    CBMD_API_END
+}
+
+extern "C" void *cbmd_stream( cbmd_ctx *ctx ) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int64_t cbmd_launch_count( cbmd_ctx *ctx ) { return ctx ? ctx->launches : 0; }
+
+extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
+{
+    CBMD_API_BEGIN
+    std::string n( name ? name : "" );
+    if ( n == "force_variant" )
+        ctx->force_variant = (int)value;
+    else
+        throw CbmdError( "unknown option: " + n );
+    CBMD_API_END
+}
+
+static void refresh_dtfm( cbmd_ctx *ctx )
+{
+    // integrator_nve_impl.h:50-54: dtf = 0.5*dt/mvv2e; dtfm = dtf/mass[type]
+    const double dtf = 0.5 * ctx->dt / ctx->mvv2e;
+    for ( int t = 0; t < CBMD_MAX_TYPES; t++ )
+        ctx->mass.dtfm[t] = dtf / ctx->mass.mass[t];
+}
+
+extern "C" int cbmd_set_units( cbmd_ctx *ctx, double boltz, double mvv2e, double dt )
+{
+    CBMD_API_BEGIN
+    ctx->boltz = boltz;
+    ctx->mvv2e = mvv2e;
+    ctx->dt = dt;
+    refresh_dtfm( ctx );
+    CBMD_API_END
+}
+
+extern "C" int cbmd_set_mass( cbmd_ctx *ctx, int ntypes, const double *mass )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( ntypes >= 1 && ntypes <= CBMD_MAX_TYPES, "ntypes out of range (1..8)" );
+    CBMD_REQUIRE( mass != nullptr, "null mass" );
+    ctx->ntypes = ntypes;
+    for ( int t = 0; t < ntypes; t++ )
+        ctx->mass.mass[t] = mass[t];
+    refresh_dtfm( ctx );
+    CBMD_API_END
+}
+
+extern "C" int cbmd_set_domain( cbmd_ctx *ctx, const double global_lo[3],
+                                const double global_hi[3], const double local_lo[3],
+                                const double local_hi[3], const double ghost_lo[3],
+                                const double ghost_hi[3], const int rank_grid[3],
+                                const int rank_pos[3] )
+{
+    CBMD_API_BEGIN
+    for ( int d = 0; d < 3; d++ )
+    {
+        ctx->glo[d] = global_lo[d];
+        ctx->ghi[d] = global_hi[d];
+        ctx->gext[d] = global_hi[d] - global_lo[d];
+        ctx->llo[d] = local_lo[d];
+        ctx->lhi[d] = local_hi[d];
+        ctx->ghost_lo[d] = ghost_lo ? ghost_lo[d] : local_lo[d];
+        ctx->ghost_hi[d] = ghost_hi ? ghost_hi[d] : local_hi[d];
+        ctx->grid[d] = rank_grid ? rank_grid[d] : 1;
+        ctx->pos[d] = rank_pos ? rank_pos[d] : 0;
+        CBMD_REQUIRE( ctx->grid[d] >= 1 && ctx->pos[d] >= 0 && ctx->pos[d] < ctx->grid[d],
+                      "bad rank grid/position" );
+    }
+    ctx->have_domain = true;
+    ctx->have_bins = false;
+    ctx->have_halo = false;
+    CBMD_API_END
+}
+
+static void upload_rows( cbmd_ctx *ctx, int first, int n, const double *x, const double *v,
+                         const double *f, const int *type, const int *id, const double *q,
+                         int id_base )
+{
+    if ( n == 0 )
+        return;
+    cudaStream_t s = ctx->stream;
+    const size_t b3 = 3 * (size_t)n * sizeof( double );
+    char *st = (char *)cbmd_scratch( ctx, b3 + (size_t)n * sizeof( int ) + 256 );
+    double *d3 = (double *)st;
+    int *dt = (int *)( st + ( ( b3 + 255 ) & ~(size_t)255 ) );
+    const int tb = 256;
+    CBMD_REQUIRE( x != nullptr, "null x" );
+    CBMD_CUDA( cudaMemcpyAsync( d3, x, b3, cudaMemcpyHostToDevice, s ) );
+    if ( type )
+        CBMD_CUDA( cudaMemcpyAsync( dt, type, (size_t)n * sizeof( int ), cudaMemcpyHostToDevice, s ) );
+    k_pack_xt<<<div_up( n, tb ), tb, 0, s>>>( ctx->xt, d3, type ? dt : nullptr, first, n );
+    CBMD_LAUNCH_CHECK( ctx );
+    if ( v )
+    {
+        CBMD_CUDA( cudaMemcpyAsync( d3, v, b3, cudaMemcpyHostToDevice, s ) );
+        k_aos_to_soa<<<div_up( 3 * n, tb ), tb, 0, s>>>( ctx->v, ctx->cap, d3, first, n );
+    }
+    else
+        k_fill3<<<div_up( n, tb ), tb, 0, s>>>( ctx->v, ctx->cap, first, n, 0.0 );
+    CBMD_LAUNCH_CHECK( ctx );
+    if ( f )
+    {
+        CBMD_CUDA( cudaMemcpyAsync( d3, f, b3, cudaMemcpyHostToDevice, s ) );
+        k_aos_to_soa<<<div_up( 3 * n, tb ), tb, 0, s>>>( ctx->f, ctx->cap, d3, first, n );
+    }
+    else
+        k_fill3<<<div_up( n, tb ), tb, 0, s>>>( ctx->f, ctx->cap, first, n, 0.0 );
+    CBMD_LAUNCH_CHECK( ctx );
+    if ( id )
+        CBMD_CUDA( cudaMemcpyAsync( ctx->id + first, id, (size_t)n * sizeof( int ),
+                                    cudaMemcpyHostToDevice, s ) );
+    else
+    {
+        k_iota<<<div_up( n, tb ), tb, 0, s>>>( ctx->id, first, n, id_base );
+        CBMD_LAUNCH_CHECK( ctx );
+    }
+    if ( q )
+        CBMD_CUDA( cudaMemcpyAsync( ctx->q + first, q, (size_t)n * sizeof( double ),
+                                    cudaMemcpyHostToDevice, s ) );
+    else
+        CBMD_CUDA( cudaMemsetAsync( ctx->q + first, 0, (size_t)n * sizeof( double ), s ) );
+    // host buffers may be pageable: make the call synchronous w.r.t. them
+    CBMD_CUDA( cudaStreamSynchronize( s ) );
+}
+
+extern "C" int cbmd_set_atoms( cbmd_ctx *ctx, int n_local, const double *x, const double *v,
+                               const double *f, const int *type, const int *id, const double *q )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( n_local >= 0, "negative atom count" );
+    ctx->n_local = 0;
+    ctx->n_ghost = 0;
+    cbmd_ensure_capacity( ctx, n_local );
+    ctx->f_zero_pending = false;
+    upload_rows( ctx, 0, n_local, x, v, f, type, id, q, 1 );
+    ctx->n_local = n_local;
+    ctx->have_halo = false;
+    ctx->nb_n = 0;
+    ctx->nb_ntot = 0;
+    CBMD_API_END
+}
+
+extern "C" int cbmd_append_ghosts( cbmd_ctx *ctx, int n, const double *x, const int *type,
+                                   const int *id )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( n >= 0, "negative ghost count" );
+    cbmd_materialize_zero_force( ctx );
+    const int first = ctx->n_local + ctx->n_ghost;
+    cbmd_ensure_capacity( ctx, first + n );
+    upload_rows( ctx, first, n, x, nullptr, nullptr, type, id, nullptr, first + 1 );
+    ctx->n_ghost += n;
+    ctx->have_halo = false; // no owner map for hand-made ghosts
+    CBMD_API_END
+}
+
+extern "C" int cbmd_set_velocities( cbmd_ctx *ctx, int n_local, const double *v )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( n_local == ctx->n_local, "velocity count != n_local" );
+    if ( n_local > 0 )
+    {
+        const size_t b3 = 3 * (size_t)n_local * sizeof( double );
+        double *d3 = (double *)cbmd_scratch( ctx, b3 );
+        CBMD_CUDA( cudaMemcpyAsync( d3, v, b3, cudaMemcpyHostToDevice, ctx->stream ) );
+        k_aos_to_soa<<<div_up( 3 * n_local, 256 ), 256, 0, ctx->stream>>>( ctx->v, ctx->cap, d3, 0,
+                                                                         n_local );
+        CBMD_LAUNCH_CHECK( ctx );
+        CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    }
+    CBMD_API_END
+}
+
+extern "C" int cbmd_get_atoms( cbmd_ctx *ctx, int first, int count, double *x, double *v,
+                               double *f, int *type, int *id, double *q )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( first >= 0 && count >= 0 && first + count <= ctx->n_local + ctx->n_ghost,
+                  "row range outside [0, n_local+n_ghost)" );
+    if ( count == 0 )
+        return 0;
+    cbmd_materialize_zero_force( ctx );
+    cudaStream_t s = ctx->stream;
+    const int tb = 256;
+    const size_t b3 = 3 * (size_t)count * sizeof( double );
+    char *st = (char *)cbmd_scratch( ctx, b3 + (size_t)count * sizeof( int ) + 256 );
+    double *d3 = (double *)st;
+    int *dt = (int *)( st + ( ( b3 + 255 ) & ~(size_t)255 ) );
+    if ( x || type )
+    {
+        k_unpack_xt<<<div_up( count, tb ), tb, 0, s>>>( ctx->xt, x ? d3 : nullptr,
+                                                        type ? dt : nullptr, first, count );
+        CBMD_LAUNCH_CHECK( ctx );
+        if ( x )
+            CBMD_CUDA( cudaMemcpyAsync( x, d3, b3, cudaMemcpyDeviceToHost, s ) );
+        if ( type )
+            CBMD_CUDA( cudaMemcpyAsync( type, dt, (size_t)count * sizeof( int ),
+                                        cudaMemcpyDeviceToHost, s ) );
+        CBMD_CUDA( cudaStreamSynchronize( s ) );
+    }
+    if ( v )
+    {
+        k_soa_to_aos<<<div_up( 3 * count, tb ), tb, 0, s>>>( ctx->v, ctx->cap, d3, first, count );
+        CBMD_LAUNCH_CHECK( ctx );
+        CBMD_CUDA( cudaMemcpyAsync( v, d3, b3, cudaMemcpyDeviceToHost, s ) );
+        CBMD_CUDA( cudaStreamSynchronize( s ) );
+    }
+    if ( f )
+    {
+        k_soa_to_aos<<<div_up( 3 * count, tb ), tb, 0, s>>>( ctx->f, ctx->cap, d3, first, count );
+        CBMD_LAUNCH_CHECK( ctx );
+        CBMD_CUDA( cudaMemcpyAsync( f, d3, b3, cudaMemcpyDeviceToHost, s ) );
+        CBMD_CUDA( cudaStreamSynchronize( s ) );
+    }
+    if ( id )
+        CBMD_CUDA( cudaMemcpyAsync( id, ctx->id + first, (size_t)count * sizeof( int ),
+                                    cudaMemcpyDeviceToHost, s ) );
+    if ( q )
+        CBMD_CUDA( cudaMemcpyAsync( q, ctx->q + first, (size_t)count * sizeof( double ),
+                                    cudaMemcpyDeviceToHost, s ) );
+    CBMD_CUDA( cudaStreamSynchronize( s ) );
+    CBMD_API_END
+}
+
+extern "C" int cbmd_get_counts( cbmd_ctx *ctx, int *n_local, int *n_ghost )
+{
+    CBMD_API_BEGIN
+    if ( n_local )
+        *n_local = ctx->n_local;
+    if ( n_ghost )
+        *n_ghost = ctx->n_ghost;
+    CBMD_API_END
+}

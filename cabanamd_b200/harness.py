@@ -1,0 +1,122 @@
+"""Python re-statement of the reference's call ORDER (CbnMD::init / run,
+cabanamd_impl.h:197-243 and :285-399) over the C ABI, for tests and bench.py.
+The product driver is the C++ host layer (cabanamd_b200/host); this harness only
+sequences the same C-ABI calls from Python."""
+import numpy as np
+
+from .capi import Context, make_domain
+
+
+def lj_tables(ntypes=1, eps=1.0, sigma=1.0, cut=2.5):
+    lj1 = np.full((ntypes, ntypes), 48.0 * eps * sigma ** 12.0)
+    lj2 = np.full((ntypes, ntypes), 24.0 * eps * sigma ** 6.0)
+    cutsq = np.full((ntypes, ntypes), cut * cut)
+    return lj1, lj2, cutsq
+
+
+def fcc_lattice(cells, density=0.8442):
+    """Positions of create_lattice's fcc branch on one rank (inputFile_impl.h:716-792):
+    loops iz, iy, ix then the 4 basis sites; x = a*(i+basis)."""
+    a = (4.0 / density) ** (1.0 / 3.0)
+    nx, ny, nz = cells
+    basis = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]], dtype=np.float64)
+    iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    cell = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], axis=1).astype(np.float64)
+    x = a * (1.0 * cell[:, None, :] + basis[None, :, :])
+    return x.reshape(-1, 3), a
+
+
+class Simulation:
+    """One rank of the MD loop on one GPU context."""
+
+    def __init__(self, ctx=None, device=0, mass=(2.0,), cut=2.5, skin=0.3, half=False,
+                 exchange_rate=20, ghost_cutoff=20.0, dt=0.005, mvv2e=1.0, boltz=1.0,
+                 max_neigh_guess=50, layout=0, nranks=1, rank=0, uid=None, eps=1.0, sigma=1.0):
+        self.ctx = ctx or Context(device)
+        self.half, self.cut, self.skin = half, cut, skin
+        self.rn = cut + skin
+        self.exchange_rate = exchange_rate
+        self.ghost_cutoff = ghost_cutoff
+        self.boltz, self.mvv2e, self.dt = boltz, mvv2e, dt
+        self.guess, self.layout = max_neigh_guess, layout
+        self.nranks, self.rank = nranks, rank
+        self.mass = np.asarray(mass, dtype=np.float64)
+        c = self.ctx
+        c.set_units(boltz, mvv2e, dt)
+        c.set_mass(self.mass)
+        c.set_lj(*lj_tables(len(self.mass), eps, sigma, cut))
+        c.comm_init(nranks, rank, uid)
+        self.step = 0
+        self.N = 0
+        self.thermo = []
+
+    def set_box(self, glo, ghi):
+        d = make_domain(glo, ghi, self.nranks, self.rank, self.ghost_cutoff)
+        self.dom = d
+        self.ctx.set_domain(d["glo"], d["ghi"], d["llo"], d["lhi"], d["ghost_lo"], d["ghost_hi"],
+                            d["grid"], d["pos"])
+
+    def set_atoms(self, x, v, type_=None, id_=None, n_global=None):
+        """Upload this rank's owned atoms (callers filter by llo <= x < lhi)."""
+        self.ctx.set_atoms(x, v, None, type_, id_)
+        n = self.ctx.reduce_sum_int(len(x)) if self.nranks > 1 else len(x)
+        self.N = n if n_global is None else n_global
+
+    def owned_mask(self, x):
+        d = self.dom
+        m = np.ones(len(x), dtype=bool)
+        for k in range(3):
+            last = d["pos"][k] == d["grid"][k] - 1
+            hi_ok = (x[:, k] <= d["lhi"][k]) if last else (x[:, k] < d["lhi"][k])
+            m &= (x[:, k] >= d["llo"][k]) & hi_ok
+        return m
+
+    # cabanamd_impl.h:197-223
+    def setup(self):
+        c = self.ctx
+        c.exchange()
+        c.bin_sort(self.rn)
+        c.exchange_halo(self.rn)
+        self.guess = c.neigh_build(self.rn, self.half, self.layout, self.guess)
+        c.zero_force()
+        c.force(self.half)
+        if self.half:
+            c.update_force()
+        self.step = 0
+
+    # cabanamd_impl.h:285-399 (one step)
+    def run(self, nsteps, thermo_rate=0):
+        c = self.ctx
+        for _ in range(nsteps):
+            self.step += 1
+            c.integrate_initial()
+            if self.step % self.exchange_rate == 0:
+                c.exchange()
+                c.bin_sort(self.rn)
+                c.exchange_halo(self.rn)
+                self.guess = c.neigh_build(self.rn, self.half, self.layout, self.guess)
+            else:
+                c.update_halo()
+            c.zero_force()
+            c.force(self.half)
+            if self.half:
+                c.update_force()
+            c.integrate_final()
+            if thermo_rate and self.step % thermo_rate == 0:
+                self.record_thermo()
+
+    # property_temperature_impl.h:55-77, property_kine_impl.h:55-76, property_pote_impl.h:55-63
+    def temperature(self):
+        s = self.ctx.reduce_sum(self.ctx.sum_mv2())
+        return s * (self.mvv2e / ((3 * self.N - 3) * self.boltz))
+
+    def kinetic(self):
+        return self.ctx.reduce_sum(self.ctx.sum_mv2()) * 0.5 * self.mvv2e
+
+    def potential(self, corrected=False):
+        pe, pe_c = self.ctx.energy(self.half)
+        return self.ctx.reduce_sum(pe_c if corrected else pe)
+
+    def record_thermo(self):
+        self.thermo.append((self.step, self.temperature(), self.potential() / self.N,
+                            self.kinetic() / self.N))

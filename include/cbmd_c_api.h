@@ -1,0 +1,153 @@
+/* include/cbmd_c_api.h — C ABI of libcbmd_cuda.so, the sm_100a implementation of
+ * CabanaMD's short-range LJ MD step.
+ *
+ * This is the drop-in boundary: every entry point replaces one method of the
+ * reference's module classes (paths relative to /root/reference/src).  Only plain
+ * pointers and sizes cross it (HOST pointers unless stated otherwise); all device
+ * memory, streams and NCCL communicators are owned by the context.  There is no
+ * CPU fallback: every call fails (non-zero) when no CUDA device is usable.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure, with a
+ * human readable message in cbmd_last_error() (thread local).  Per-atom host
+ * arrays are row-major [n][3] doubles for x/v/f and int32 for type/id, i.e. the
+ * layout of the reference's slices.  Atoms [0, n_local) are owned, then
+ * [n_local, n_local + n_ghost) are ghosts, as in system.h:73-76.
+ */
+#ifndef CBMD_C_API_H
+#define CBMD_C_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+    typedef struct cbmd_ctx cbmd_ctx;
+
+    enum
+    {
+        CBMD_LAYOUT_2D = 0, /* Cabana::VerletLayout2D  (--neigh-type VERLET_2D)  */
+        CBMD_LAYOUT_CSR = 1 /* Cabana::VerletLayoutCSR (--neigh-type VERLET_CSR) */
+    };
+
+    /* ---- life cycle / errors --------------------------------------------------
+     * replaces: Kokkos::ScopeGuard + `new t_System; system->init()`
+     * (bin/main.cpp:65, cabanamd_impl.h:74-75). */
+    int cbmd_create( cbmd_ctx **out, int device );
+    int cbmd_destroy( cbmd_ctx *ctx );
+    const char *cbmd_last_error( void );
+    const char *cbmd_version( void );
+    /* blocks until all queued device work of this context is done (Kokkos::fence,
+     * force_lj_cabana_neigh_impl.h:117) */
+    int cbmd_sync( cbmd_ctx *ctx );
+
+    /* ---- System (system.h:65-279, system_types/system_1aosoa.h) --------------- */
+    /* units: system->boltz/mvv2e/dt (inputFile_impl.h:146-176) */
+    int cbmd_set_units( cbmd_ctx *ctx, double boltz, double mvv2e, double dt );
+    /* per-type masses: system->mass (system.h:83-86, inputFile_impl.h:304-314) */
+    int cbmd_set_mass( cbmd_ctx *ctx, int ntypes, const double *mass );
+    /* domain scalars produced by SystemCommon::create_domain (system.h:149-205,
+     * 251-271): global box, this rank's own box, ghost-mesh box, rank grid/position */
+    int cbmd_set_domain( cbmd_ctx *ctx, const double global_lo[3], const double global_hi[3],
+                         const double local_lo[3], const double local_hi[3],
+                         const double ghost_lo[3], const double ghost_hi[3], const int rank_grid[3],
+                         const int rank_pos[3] );
+    /* upload owned atoms and set N_local = n, N_ghost = 0 (System::resize +
+     * deep_copy from the host system, inputFile_impl.h:786-791,851).  v, f, id, q
+     * may be NULL (zero / 1..n / zero). */
+    int cbmd_set_atoms( cbmd_ctx *ctx, int n_local, const double *x, const double *v,
+                        const double *f, const int *type, const int *id, const double *q );
+    /* append n ghosts (x, type[, id]) after the current atoms — test hook matching
+     * the unit tests' "last num_ghost atoms are ghosts" set-up (tstNeighbor.hpp:262-264) */
+    int cbmd_append_ghosts( cbmd_ctx *ctx, int n, const double *x, const int *type,
+                            const int *id );
+    /* download rows [first, first+count) (any pointer may be NULL) */
+    int cbmd_get_atoms( cbmd_ctx *ctx, int first, int count, double *x, double *v, double *f,
+                        int *type, int *id, double *q );
+    /* overwrite v of owned atoms [0,n_local) (velocity rescale, inputFile_impl.h:858-865) */
+    int cbmd_set_velocities( cbmd_ctx *ctx, int n_local, const double *v );
+    int cbmd_get_counts( cbmd_ctx *ctx, int *n_local, int *n_ghost );
+
+    /* ---- Integrator (integrator_nve.h:91-110, integrator_nve_impl.h:50-83) ---- */
+    int cbmd_integrate_initial( cbmd_ctx *ctx );
+    int cbmd_integrate_final( cbmd_ctx *ctx );
+
+    /* ---- Binning (binning_cabana_impl.h:57-113) --------------------------------
+     * Binning::create_binning(dx,dy,dz,halo_depth,do_local=true,do_ghost=false,
+     * sort=true): cell-sorts the owned atoms and permutes all six fields.  Outputs
+     * (may be NULL) are the public members nbinx/y/z, minx..maxz. */
+    int cbmd_bin_sort( cbmd_ctx *ctx, double dx, double dy, double dz, int halo_depth,
+                       int nbin_out[3], double min_out[3], double max_out[3] );
+    /* permutation applied by the last cbmd_bin_sort: new[i] = old[perm[i]] */
+    int cbmd_get_permutation( cbmd_ctx *ctx, int *perm );
+
+    /* ---- Neighbor (neighbor_verlet.h:43-62, [Cabana] VerletList) ---------------
+     * NeighborVerlet::create: rows [0,n_local) over all n_local+n_ghost atoms,
+     * d^2 <= rcut^2 inclusive; half != 0 selects Cabana::HalfNeighborTag.
+     * max_neigh_guess is the initial row capacity ("neigh_modify one"); the value
+     * actually used/regrown (current_max * 1.1) is returned like
+     * neighbor_verlet.h:58-61. */
+    int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layout, int max_neigh_guess,
+                          int *max_neigh_guess_out );
+    /* NeighborList<>::maxNeighbor / total stored neighbours */
+    int cbmd_neigh_sizes( cbmd_ctx *ctx, int64_t *total, int *max_neigh );
+    /* host copy in CSR form: counts[n_local+n_ghost] (ghost rows 0),
+     * offsets[n_local+1], neighbors[total]; equivalent of walking
+     * numNeighbor/getNeighbor (tstNeighbor.hpp:55-73) */
+    int cbmd_neigh_get( cbmd_ctx *ctx, int *counts, int64_t *offsets, int *neighbors );
+
+    /* ---- Force (force.h:57-74, force_lj_cabana_neigh_impl.h) -------------------- */
+    /* ForceLJ::init_coeff result tables, ntypes x ntypes row-major (:62-89) */
+    int cbmd_set_lj( cbmd_ctx *ctx, int ntypes, const double *lj1, const double *lj2,
+                     const double *cutsq );
+    /* Cabana::deep_copy(f, 0.0) over owned+ghost atoms (cabanamd_impl.h:213-215,336-338) */
+    int cbmd_zero_force( cbmd_ctx *ctx );
+    /* ForceLJ::compute: accumulates into f; half != 0 => Newton-3 path, also
+     * updating ghost f (:205-259) */
+    int cbmd_force_lj( cbmd_ctx *ctx, int half );
+    /* ForceLJ::compute_energy: shifted pair energy of this rank (:261-377).
+     * pe_corrected (may be NULL): half-list energy with fac=1 for every stored pair
+     * (SURVEY Appendix B.4); equals *pe for full lists. */
+    int cbmd_energy_lj( cbmd_ctx *ctx, int half, double *pe, double *pe_corrected );
+
+    /* ---- Comm (comm_mpi.h:125-138, comm_mpi_impl.h) ----------------------------- */
+    /* 128-byte NCCL unique id created on rank 0 and handed to every rank out of band */
+    int cbmd_comm_unique_id( void *id128 );
+    /* Comm ctor + create_domain_decomposition (:52-119): NCCL communicator over
+     * nranks (one process per GPU); nranks == 1 needs no id (may be NULL). */
+    int cbmd_comm_init( cbmd_ctx *ctx, int nranks, int rank, const void *id128 );
+    int cbmd_comm_rank( cbmd_ctx *ctx, int *rank, int *nranks );
+    /* Comm::exchange (:191-278): drop ghosts, PBC-wrap / migrate owned atoms;
+     * returns the global number of migrated atoms */
+    int cbmd_exchange( cbmd_ctx *ctx, int *n_sent_global );
+    /* Comm::exchange_halo (:280-367): 6-phase ghost build with shell depth comm_depth */
+    int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth );
+    /* Comm::update_halo (:369-408): refresh ghost positions */
+    int cbmd_update_halo( cbmd_ctx *ctx );
+    /* Comm::update_force (:410-441): add ghost forces back into their owners */
+    int cbmd_update_force( cbmd_ctx *ctx );
+    /* Comm::reduce_float / reduce_int / reduce_max_* / scan_int (:121-189), in place */
+    int cbmd_reduce_sum_double( cbmd_ctx *ctx, double *vals, int count );
+    int cbmd_reduce_sum_int( cbmd_ctx *ctx, int *vals, int count );
+    int cbmd_reduce_max_double( cbmd_ctx *ctx, double *vals, int count );
+    int cbmd_reduce_max_int( cbmd_ctx *ctx, int *vals, int count );
+    int cbmd_scan_sum_int( cbmd_ctx *ctx, int *vals, int count );
+
+    /* ---- thermo (property_temperature.h:73-79, property_kine.h:72-78) ---------- */
+    /* sum over owned atoms of m v^2 (this rank only; callers reduce + scale) */
+    int cbmd_sum_mv2( cbmd_ctx *ctx, double *sum );
+
+    /* ---- measurement hooks (no reference equivalent) --------------------------- */
+    /* the context's compute stream as a cudaStream_t, for CUDA-event timing */
+    void *cbmd_stream( cbmd_ctx *ctx );
+    /* number of kernels launched by this context since creation */
+    int64_t cbmd_launch_count( cbmd_ctx *ctx );
+    /* kernel variant switches for A/B measurements, e.g. "force_variant"=0|1 */
+    int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value );
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBMD_C_API_H */

@@ -1,0 +1,340 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Tolerances (north_star): neighbour sets bit-exact
+after sorting; per-atom forces <= 1e-10 relative (FP64); integrator and ghost
+refresh bit-identical; thermo to round-off."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+FORCE_RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import cabanamd_b200 as cb
+
+    return cb
+
+
+def tst_neighbor_config(seed=342343901):
+    rc = 2.32
+    lo, hi = -5.3 * rc, 4.7 * rc
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(lo, hi, size=(1000, 3))
+    return x, 800, rc, lo, hi
+
+
+def gpu_rows(ctx):
+    counts, offsets, neigh = ctx.neigh_get()
+    nl, _ = ctx.counts()
+    return counts, [np.sort(neigh[offsets[i]:offsets[i + 1]]) for i in range(nl)]
+
+
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("guess", [100, 7])
+def test_tstneighbor_bitexact(cb, half, layout, guess):
+    """unit_test/tstNeighbor.hpp:322-379 restated: set == O(N^2) brute force (and the
+    exact half criterion), ghost rows empty; guess=7 exercises the 2-D regrow path."""
+    x, n_local, rc, lo, hi = tst_neighbor_config()
+    ctx = cb.Context(0)
+    ctx.set_domain([lo] * 3, [hi] * 3)
+    ctx.set_atoms(x[:n_local])
+    ctx.append_ghosts(x[n_local:])
+    g = ctx.neigh_build(rc, half, layout, guess)
+    ref = O.NeighList().brute(x, n_local, rc, half)
+    rc_counts, _, _ = ref.arrays()
+    counts, rows = gpu_rows(ctx)
+    assert np.array_equal(counts, rc_counts)
+    assert np.all(counts[n_local:] == 0)
+    for a, b in zip(rows, ref.rows_sorted()):
+        assert np.array_equal(a, b)
+    assert g >= counts.max()
+    tot, mx = ctx.neigh_sizes()
+    assert tot == counts.sum() and mx == counts.max()
+
+
+def test_neighbor_edge_cases(cb):
+    ctx = cb.Context(0)
+    ctx.set_domain([0.0] * 3, [10.0] * 3)
+    # empty system
+    ctx.set_atoms(np.zeros((0, 3)))
+    ctx.neigh_build(2.8, False, 0, 10)
+    c, o, n = ctx.neigh_get()
+    assert len(c) == 0 and len(n) == 0
+    # one atom, and coincident-coordinate ties for the half discriminator
+    x = np.array([[1.0, 1.0, 1.0], [1.0, 1.0, 2.0], [1.0, 2.0, 1.0], [3.8, 1.0, 1.0],
+                  [3.8000001, 1.0, 1.0], [9.9, 9.9, 9.9]])
+    for half in (False, True):
+        ctx.set_atoms(x)
+        ctx.neigh_build(2.8, half, 0, 2)
+        ref = O.NeighList().brute(x, len(x), 2.8, half)
+        counts, rows = gpu_rows(ctx)
+        for a, b in zip(rows, ref.rows_sorted()):
+            assert np.array_equal(a, b)
+    # exact-cutoff pair: d^2 == rc^2 is inside (inclusive), list is stale after set_atoms
+    x = np.array([[0.0, 0.0, 0.0], [3.0, 4.0, 0.0]])
+    ctx.set_atoms(x)
+    with pytest.raises(cb.CbmdError):
+        ctx.force(False)
+    ctx.neigh_build(5.0, False, 0, 4)
+    counts, rows = gpu_rows(ctx)
+    assert counts.tolist() == [1, 1]
+
+
+def test_integrator_bitexact_and_reversible(cb):
+    """unit_test/tstIntegrator.hpp:83-137 + bit equality with the oracle."""
+    rng = np.random.default_rng(11)
+    n = 1000
+    x0 = rng.uniform(0, 20, size=(n, 3))
+    v0 = rng.uniform(-1, 1, size=(n, 3))
+    f0 = rng.uniform(-1, 1, size=(n, 3))
+    t = rng.integers(0, 2, size=n).astype(np.int32)
+    mass = [1.0, 3.0]
+    ctx = cb.Context(0)
+    ctx.set_units(1.0, 1.0, 0.005)
+    ctx.set_mass(mass)
+    ctx.set_domain([0.0] * 3, [20.0] * 3)
+    ctx.set_atoms(x0, v0, f0, t)
+    x, v = x0, v0
+    for _ in range(100):
+        ctx.integrate_initial()
+        ctx.integrate_final()
+        x, v = O.integrate(0, x, v, f0, t, mass)
+        x, v = O.integrate(1, x, v, f0, t, mass)
+    a = ctx.get_atoms()
+    assert np.array_equal(a["x"], x) and np.array_equal(a["v"], v)
+    assert np.array_equal(a["f"], f0) and np.array_equal(a["type"], t)
+    ctx.set_velocities(-a["v"])
+    for _ in range(100):
+        ctx.integrate_initial()
+        ctx.integrate_final()
+    b = ctx.get_atoms()
+    assert np.allclose(b["x"].astype(np.float32), x0.astype(np.float32), rtol=5e-7, atol=0)
+
+
+def melted_state(cells=(10, 10, 10), steps=60, half=False):
+    """A liquid-like configuration from the oracle (lattice + a few dozen steps)."""
+    s = O.Sim(mass=[2.0], half=half).create_lattice_fcc(cells=cells).setup()
+    s.run(steps)
+    return s
+
+
+def test_binning_matches_oracle(cb):
+    s = melted_state((8, 8, 8), 25)
+    d = s.get()
+    n = d["n_local"]
+    dom = s.domain()
+    ctx = cb.Context(0)
+    ctx.set_domain(dom["llo"], dom["lhi"])
+    ctx.set_atoms(d["x"][:n], d["v"][:n], d["f"][:n], d["type"][:n], d["id"][:n])
+    nbin, mn, mx = ctx.bin_sort(2.8)
+    perm, onbin, omn, omx = O.binning(d["x"][:n], dom["llo"], dom["lhi"], 2.8)
+    assert np.array_equal(nbin, onbin) and np.array_equal(mn, omn) and np.array_equal(mx, omx)
+    assert np.array_equal(ctx.permutation(), perm)
+    a = ctx.get_atoms()
+    for k in ("x", "v", "f"):
+        assert np.array_equal(a[k], d[k][:n][perm])
+    assert np.array_equal(a["id"], d["id"][:n][perm])
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_force_energy_on_oracle_state(cb, half):
+    """Same atoms (owned + ghosts from the oracle's 6-phase build): neighbour sets
+    bit-exact, forces <= 1e-10 relative, energy to round-off."""
+    s = melted_state((10, 10, 10), 60, half)
+    d = s.get()
+    n, ng = d["n_local"], d["n_ghost"]
+    dom = s.domain()
+    lj1, lj2, cutsq = s.tables
+    ctx = cb.Context(0)
+    ctx.set_mass([2.0])
+    ctx.set_lj(lj1, lj2, cutsq)
+    ctx.set_domain(dom["llo"], dom["lhi"])
+    ctx.set_atoms(d["x"][:n], d["v"][:n], None, d["type"][:n], d["id"][:n])
+    ctx.append_ghosts(d["x"][n:], d["type"][n:], d["id"][n:])
+    ctx.neigh_build(2.8, half, 0, 50)
+    counts, rows = gpu_rows(ctx)
+    ocounts, ooff, oneigh = s.list()
+    assert np.array_equal(counts, ocounts)
+    for i in range(n):
+        assert np.array_equal(rows[i], np.sort(oneigh[ooff[i]:ooff[i + 1]]))
+    # oracle force on its own list, before the reverse ghost fold (raw kernel output)
+    ol = O.NeighList().set(n, n + ng, ocounts, ooff, oneigh)
+    f_ref = ol.force(d["x"], d["type"], half, lj1, lj2, cutsq)
+    ctx.zero_force()
+    ctx.force(half)
+    a = ctx.get_atoms()
+    scale = np.abs(f_ref).max()
+    assert np.abs(a["f"] - f_ref).max() <= FORCE_RTOL * scale
+    nz = np.abs(f_ref) > 1e-3 * scale
+    assert (np.abs(a["f"] - f_ref)[nz] / np.abs(f_ref)[nz]).max() <= FORCE_RTOL
+    pe, pe_c = ctx.energy(half)
+    e_ref = ol.energy(d["x"], d["type"], half, lj1, lj2, cutsq)
+    e_cor = ol.energy(d["x"], d["type"], half, lj1, lj2, cutsq, corrected=True)
+    assert abs(pe - e_ref) <= 1e-12 * abs(e_ref)
+    assert abs(pe_c - e_cor) <= 1e-12 * abs(e_cor)
+    # accumulate semantics: a second compute without zeroing doubles f
+    ctx.force(half)
+    b = ctx.get_atoms()
+    assert np.abs(b["f"] - 2 * a["f"]).max() <= 1e-12 * scale
+
+
+def test_multitype_force(cb):
+    rng = np.random.default_rng(5)
+    s = melted_state((8, 8, 8), 40)
+    d = s.get()
+    n, ng = d["n_local"], d["n_ghost"]
+    nt = 3
+    t = rng.integers(0, nt, size=n + ng).astype(np.int32)
+    lj1 = rng.uniform(20, 60, size=(nt, nt))
+    lj1 = (lj1 + lj1.T) / 2
+    lj2 = rng.uniform(10, 30, size=(nt, nt))
+    lj2 = (lj2 + lj2.T) / 2
+    cutsq = rng.uniform(4.0, 6.25, size=(nt, nt))
+    cutsq = (cutsq + cutsq.T) / 2
+    dom = s.domain()
+    ctx = cb.Context(0)
+    ctx.set_mass([1.0, 2.0, 3.0])
+    ctx.set_lj(lj1, lj2, cutsq)
+    ctx.set_domain(dom["llo"], dom["lhi"])
+    ctx.set_atoms(d["x"][:n], None, None, t[:n])
+    ctx.append_ghosts(d["x"][n:], t[n:])
+    ctx.neigh_build(2.8, False, 0, 90)
+    oc, oo, on = s.list()
+    ol = O.NeighList().set(n, n + ng, oc, oo, on)
+    f_ref = ol.force(d["x"], t, False, lj1, lj2, cutsq)
+    ctx.zero_force()
+    ctx.force(False)
+    a = ctx.get_atoms()
+    assert np.abs(a["f"] - f_ref).max() <= FORCE_RTOL * np.abs(f_ref).max()
+    pe, _ = ctx.energy(False)
+    e_ref = ol.energy(d["x"], t, False, lj1, lj2, cutsq)
+    assert abs(pe - e_ref) <= 1e-12 * abs(e_ref)
+
+
+def canon(x, ids):
+    o = np.argsort(ids, kind="stable")
+    return x[o], ids[o]
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_halo_build_and_update_match_oracle(cb, half):
+    """T6: ghost set == oracle's 6-phase set (same order: ordered compaction), and
+    update_halo is bitwise owner + shift."""
+    from cabanamd_b200.harness import Simulation
+
+    s = melted_state((8, 8, 8), 19, half)
+    d = s.get()
+    n = d["n_local"]
+    dom = s.domain()
+    sim = Simulation(half=half)
+    sim.set_box(dom["llo"], dom["lhi"])
+    sim.set_atoms(d["x"][:n], d["v"][:n], d["type"][:n], d["id"][:n])
+    # oracle: one more step hits the rebuild at step 20
+    s.run(1)
+    sim.ctx.set_atoms(d["x"][:n], d["v"][:n], d["f"][:n], d["type"][:n], d["id"][:n])
+    sim.step = 19
+    sim.run(1)
+    o = s.get()
+    a = sim.ctx.get_atoms()
+    assert a["n_local"] == o["n_local"] and a["n_ghost"] == o["n_ghost"]
+    assert np.array_equal(a["id"], o["id"])  # same owned order AND same ghost order
+    assert np.array_equal(a["x"], o["x"])  # bitwise: integrate + wrap + sort + ghosts
+    # three more steps: update_halo path
+    s.run(3)
+    sim.run(3)
+    o = s.get()
+    a = sim.ctx.get_atoms()
+    assert np.array_equal(a["id"], o["id"])
+    assert np.abs(a["x"] - o["x"]).max() < 1e-12
+    # ghosts are exact images of their owners
+    nl = a["n_local"]
+    L = dom["lhi"] - dom["llo"]
+    pos_of = {i: k for k, i in enumerate(a["id"][:nl])}
+    own = np.array([pos_of[i] for i in a["id"][nl:]])
+    delta = (a["x"][nl:] - a["x"][own]) / L
+    assert np.array_equal(delta, np.round(delta))
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_trajectory_and_thermo_match_oracle(cb, half):
+    """T8 (short form; the 1000-step form runs in bench/): same initial state, 100
+    steps with rebuilds every 20: thermo agrees to round-off growth, ids identical."""
+    from cabanamd_b200.harness import Simulation
+
+    s0 = O.Sim(mass=[2.0], half=half).create_lattice_fcc(cells=(10, 10, 10))
+    d = s0.get()
+    dom = s0.domain()
+    s0.setup()
+    sim = Simulation(half=half)
+    sim.set_box(dom["llo"], dom["lhi"])
+    sim.set_atoms(d["x"], d["v"], d["type"], d["id"])
+    sim.setup()
+    s0.record_thermo()
+    sim.record_thermo()
+    s0.run(100, 10)
+    sim.run(100, 10)
+    tg, to = np.array(sim.thermo), np.array(s0.thermo())
+    assert np.array_equal(tg[:, 0], to[:, 0])
+    assert np.abs(tg[:, 1:] - to[:, 1:]).max() < 1e-9
+    # step-0 values are exact to round-off
+    assert np.abs(tg[0, 1:] - to[0, 1:]).max() < 1e-13
+    a, o = sim.ctx.get_atoms(), s0.get()
+    assert np.array_equal(np.sort(a["id"][: a["n_local"]]), np.sort(o["id"][: o["n_local"]]))
+    xa, _ = canon(a["x"][: a["n_local"]], a["id"][: a["n_local"]])
+    xo, _ = canon(o["x"][: o["n_local"]], o["id"][: o["n_local"]])
+    assert np.abs(xa - xo).max() < 1e-8
+
+
+def test_inlj_step0_known_answer_gpu(cb):
+    """T5: in.lj (256 000 atoms) step-0 thermo: 1.400000 / -6.332812 / -4.232820."""
+    from cabanamd_b200.harness import Simulation, fcc_lattice
+
+    s0 = O.Sim(mass=[2.0]).create_lattice_fcc(cells=(40, 40, 40))
+    d = s0.get()
+    x, a = fcc_lattice((40, 40, 40))
+    assert np.array_equal(x, d["x"])  # harness lattice == oracle lattice, bitwise
+    dom = s0.domain()
+    sim = Simulation()
+    sim.set_box(dom["llo"], dom["lhi"])
+    sim.set_atoms(d["x"], d["v"], d["type"], d["id"])
+    sim.setup()
+    T, pe, ke = sim.temperature(), sim.potential() / sim.N, sim.kinetic() / sim.N
+    assert f"{T:.6f}" == "1.400000"
+    assert f"{pe:.6f}" == "-6.332812"
+    assert f"{pe + ke:.6f}" == "-4.232820"
+    counts, _, _ = sim.ctx.neigh_get()
+    assert np.all(counts[:256000] == 78)
+    assert sim.guess == int(78 * 1.1)
+
+
+def test_newton3_properties_full_size(cb):
+    """Size-independent properties at the bench size (1 M atoms): sum f = 0, half ==
+    full after the reverse fold, neighbour symmetry via counts."""
+    from cabanamd_b200.harness import Simulation, fcc_lattice
+
+    x, a = fcc_lattice((63, 63, 63))
+    rng = np.random.default_rng(1)
+    x = x + rng.uniform(-0.05, 0.05, size=x.shape)
+    L = 63 * a
+    x = np.mod(x, L)
+    out = {}
+    for half in (False, True):
+        sim = Simulation(half=half, max_neigh_guess=100)
+        sim.set_box([0.0] * 3, [L] * 3)
+        sim.set_atoms(x, np.zeros_like(x))
+        sim.setup()
+        g = sim.ctx.get_atoms(fields="fi")
+        nl = g["n_local"]
+        o = np.argsort(g["id"][:nl])
+        out[half] = g["f"][:nl][o]
+        tot, mx = sim.ctx.neigh_sizes()
+        out[("tot", half)] = tot
+    scale = np.abs(out[False]).max()
+    assert np.abs(out[False].sum(axis=0)).max() < 1e-9 * scale * 1000
+    assert np.abs(out[False] - out[True]).max() < 1e-10 * scale
+    assert out[("tot", False)] == 2 * out[("tot", True)]
