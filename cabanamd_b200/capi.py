@@ -98,6 +98,9 @@ def load_library():
     L.cbmd_launch_count.argtypes = [vp]
     L.cbmd_launch_count.restype = C.c_int64
     L.cbmd_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    L.cbmd_timing_enable.argtypes = [vp, C.c_int]
+    L.cbmd_timing_get.argtypes = [vp, C.c_int, c_dp, c_lp]
+    L.cbmd_timing_reset.argtypes = [vp]
     _LIB = L
     return L
 
@@ -339,6 +342,23 @@ class Context:
 
     def launch_count(self):
         return self.L.cbmd_launch_count(self.h)
+
+    BUCKETS = ("force", "neigh", "comm", "integrate", "other", "force_kernel")
+
+    def timing_enable(self, on=True):
+        self._ck(self.L.cbmd_timing_enable(self.h, int(on)))
+
+    def timing_reset(self):
+        self._ck(self.L.cbmd_timing_reset(self.h))
+
+    def timing(self):
+        """{bucket: (milliseconds, regions)} accumulated since the last reset."""
+        out = {}
+        for b, name in enumerate(self.BUCKETS):
+            ms, n = C.c_double(), C.c_int64()
+            self._ck(self.L.cbmd_timing_get(self.h, b, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
 
     def set_option(self, name, value):
         self._ck(self.L.cbmd_set_option(self.h, name.encode(), float(value)))

@@ -214,6 +214,7 @@ extern "C" int cbmd_bin_sort( cbmd_ctx *ctx, double dx, double dy, double dz, in
                               int nbin_out[3], double min_out[3], double max_out[3] )
 {
     CBMD_API_BEGIN
+    TimedRegion timed__( ctx, CBMD_T_OTHER );
     CBMD_REQUIRE( ctx->have_domain, "cbmd_set_domain must be called before cbmd_bin_sort" );
     CBMD_REQUIRE( dx > 0 && dy > 0 && dz > 0, "bin sizes must be positive" );
     cbmd_materialize_zero_force( ctx );

@@ -273,6 +273,7 @@ static void phase_peers( const cbmd_ctx *ctx, int ph, int &peer_send, int &peer_
 extern "C" int cbmd_exchange( cbmd_ctx *ctx, int *n_sent_global )
 {
     CBMD_API_BEGIN
+    TimedRegion timed__( ctx, CBMD_T_COMM );
     CBMD_REQUIRE( ctx->have_domain, "cbmd_set_domain must be called before cbmd_exchange" );
     cbmd_materialize_zero_force( ctx );
     cudaStream_t s = ctx->stream;
@@ -421,6 +422,7 @@ __global__ void __launch_bounds__( 256 )
 extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
 {
     CBMD_API_BEGIN
+    TimedRegion timed__( ctx, CBMD_T_COMM );
     CBMD_REQUIRE( ctx->have_domain, "cbmd_set_domain must be called before cbmd_exchange_halo" );
     CBMD_REQUIRE( comm_depth > 0, "comm depth must be positive" );
     cbmd_materialize_zero_force( ctx );
@@ -574,6 +576,7 @@ __global__ void __launch_bounds__( 256 )
 extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
 {
     CBMD_API_BEGIN
+    TimedRegion timed__( ctx, CBMD_T_COMM );
     CBMD_REQUIRE( ctx->have_halo, "cbmd_exchange_halo must be called before cbmd_update_halo" );
     cudaStream_t s = ctx->stream;
     if ( ctx->n_ghost == 0 )
@@ -646,6 +649,7 @@ __global__ void __launch_bounds__( 256 )
 extern "C" int cbmd_update_force( cbmd_ctx *ctx )
 {
     CBMD_API_BEGIN
+    TimedRegion timed__( ctx, CBMD_T_COMM );
     CBMD_REQUIRE( ctx->have_halo, "cbmd_exchange_halo must be called before cbmd_update_force" );
     cbmd_materialize_zero_force( ctx );
     cudaStream_t s = ctx->stream;

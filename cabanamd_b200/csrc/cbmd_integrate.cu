@@ -51,6 +51,7 @@ __global__ void __launch_bounds__( 256 )
 extern "C" int cbmd_integrate_initial( cbmd_ctx *ctx )
 {
     CBMD_API_BEGIN
+    TimedRegion timed__( ctx, CBMD_T_INTEGRATE );
     cbmd_materialize_zero_force( ctx );
     const int n = ctx->n_local;
     if ( n > 0 )
@@ -66,6 +67,7 @@ extern "C" int cbmd_integrate_initial( cbmd_ctx *ctx )
 extern "C" int cbmd_integrate_final( cbmd_ctx *ctx )
 {
     CBMD_API_BEGIN
+    TimedRegion timed__( ctx, CBMD_T_INTEGRATE );
     cbmd_materialize_zero_force( ctx );
     const int n = ctx->n_local;
     if ( n > 0 )
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__( 256 )
 extern "C" int cbmd_sum_mv2( cbmd_ctx *ctx, double *sum )
 {
     CBMD_API_BEGIN
+    TimedRegion timed__( ctx, CBMD_T_OTHER );
     CBMD_REQUIRE( sum != nullptr, "null output" );
     const int n = ctx->n_local;
     if ( n == 0 )

@@ -123,6 +123,54 @@ struct cbmd_ctx
 
     // options
     int force_variant = 0;
+
+    // CUDA-event timers (cbmd_timing_*)
+    bool timing = false;
+    struct Bucket
+    {
+        std::vector<cudaEvent_t> pending; // start,end,start,end,...
+        double ms = 0.0;
+        int64_t count = 0;
+    } bucket[CBMD_T_NBUCKETS];
+    std::vector<cudaEvent_t> event_pool;
+};
+
+// RAII timed region on the context stream
+struct TimedRegion
+{
+    cbmd_ctx *ctx;
+    int b;
+    cudaEvent_t e1 = nullptr;
+    static cudaEvent_t get( cbmd_ctx *c )
+    {
+        cudaEvent_t e;
+        if ( !c->event_pool.empty() )
+        {
+            e = c->event_pool.back();
+            c->event_pool.pop_back();
+        }
+        else
+            cudaEventCreate( &e );
+        return e;
+    }
+    TimedRegion( cbmd_ctx *c, int bucket )
+        : ctx( c )
+        , b( bucket )
+    {
+        if ( !ctx->timing )
+            return;
+        cudaEvent_t e0 = get( ctx );
+        e1 = get( ctx );
+        cudaEventRecord( e0, ctx->stream );
+        ctx->bucket[b].pending.push_back( e0 );
+    }
+    ~TimedRegion()
+    {
+        if ( !e1 )
+            return;
+        cudaEventRecord( e1, ctx->stream );
+        ctx->bucket[b].pending.push_back( e1 );
+    }
 };
 
 // ---------------------------------------------------------------------------

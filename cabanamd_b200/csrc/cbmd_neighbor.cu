@@ -97,6 +97,7 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
                                  int max_neigh_guess, int *max_neigh_guess_out )
 {
     CBMD_API_BEGIN
+    TimedRegion timed__( ctx, CBMD_T_NEIGH );
     CBMD_REQUIRE( ctx->have_domain, "cbmd_set_domain must be called before cbmd_neigh_build" );
     CBMD_REQUIRE( rcut > 0, "neighbour cutoff must be positive" );
     CBMD_REQUIRE( layout == CBMD_LAYOUT_2D || layout == CBMD_LAYOUT_CSR, "unknown list layout" );

@@ -259,6 +259,11 @@ extern "C" int cbmd_destroy( cbmd_ctx *ctx )
         cudaFreeHost( ctx->h_pinned_i );
     if ( ctx->nccl )
         ncclCommDestroy( ctx->nccl );
+    for ( int b = 0; b < CBMD_T_NBUCKETS; b++ )
+        for ( cudaEvent_t e : ctx->bucket[b].pending )
+            cudaEventDestroy( e );
+    for ( cudaEvent_t e : ctx->event_pool )
+        cudaEventDestroy( e );
     cudaStreamDestroy( ctx->stream );
     delete ctx;
     return 0;
@@ -282,6 +287,58 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
         ctx->force_variant = (int)value;
     else
         throw CbmdError( "unknown option: " + n );
+    CBMD_API_END
+}
+
+static void timing_drain( cbmd_ctx *ctx )
+{
+    CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    for ( int b = 0; b < CBMD_T_NBUCKETS; b++ )
+    {
+        auto &B = ctx->bucket[b];
+        for ( size_t k = 0; k + 1 < B.pending.size(); k += 2 )
+        {
+            float ms = 0.f;
+            CBMD_CUDA( cudaEventElapsedTime( &ms, B.pending[k], B.pending[k + 1] ) );
+            B.ms += ms;
+            B.count++;
+            ctx->event_pool.push_back( B.pending[k] );
+            ctx->event_pool.push_back( B.pending[k + 1] );
+        }
+        B.pending.clear();
+    }
+}
+
+extern "C" int cbmd_timing_enable( cbmd_ctx *ctx, int on )
+{
+    CBMD_API_BEGIN
+    if ( !on )
+        timing_drain( ctx );
+    ctx->timing = on != 0;
+    CBMD_API_END
+}
+
+extern "C" int cbmd_timing_get( cbmd_ctx *ctx, int bucket, double *ms, int64_t *count )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( bucket >= 0 && bucket < CBMD_T_NBUCKETS, "bad timing bucket" );
+    timing_drain( ctx );
+    if ( ms )
+        *ms = ctx->bucket[bucket].ms;
+    if ( count )
+        *count = ctx->bucket[bucket].count;
+    CBMD_API_END
+}
+
+extern "C" int cbmd_timing_reset( cbmd_ctx *ctx )
+{
+    CBMD_API_BEGIN
+    timing_drain( ctx );
+    for ( int b = 0; b < CBMD_T_NBUCKETS; b++ )
+    {
+        ctx->bucket[b].ms = 0.0;
+        ctx->bucket[b].count = 0;
+    }
     CBMD_API_END
 }
 

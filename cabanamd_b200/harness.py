@@ -120,3 +120,61 @@ class Simulation:
     def record_thermo(self):
         self.thermo.append((self.step, self.temperature(), self.potential() / self.N,
                             self.kinetic() / self.N))
+
+
+def velocity_geom_uniform(x, seed):
+    """Vectorised LAMMPS_RandomVelocityGeom (inputFile.h:73-148): per atom, seed =
+    Jenkins one-at-a-time hash of the 4 bytes of `seed` and the 24 bytes of (x,y,z)
+    (bytes added as SIGNED char), masked to 27 bits; 5 warm-up draws; returns the
+    three uniform() draws per atom."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.shape[0]
+    M = np.uint64(0xFFFFFFFF)
+    h = np.zeros(n, dtype=np.uint64)
+
+    def mix(h, byte_vals):
+        # hash += (signed char) b  -> as unsigned 32-bit wraparound
+        h = (h + (byte_vals.astype(np.int64).astype(np.uint64) & M)) & M
+        h = (h + ((h << np.uint64(10)) & M)) & M
+        h = h ^ (h >> np.uint64(6))
+        return h
+
+    sb = np.frombuffer(np.array([seed], dtype=np.int32).tobytes(), dtype=np.int8)
+    for b in sb:
+        h = mix(h, np.full(n, b, dtype=np.int8))
+    xb = x.view(np.int8).reshape(n, 24)
+    for k in range(24):
+        h = mix(h, xb[:, k])
+    h = (h + ((h << np.uint64(3)) & M)) & M
+    h = h ^ (h >> np.uint64(11))
+    h = (h + ((h << np.uint64(15)) & M)) & M
+    s = (h & np.uint64(0x7FFFFFF)).astype(np.int64)
+    s[s == 0] = 1
+    IA, IM, IQ, IR = 16807, 2147483647, 127773, 2836
+
+    def draw(s):
+        k = s // IQ
+        s = IA * (s - k * IQ) - IR * k
+        s = np.where(s < 0, s + IM, s)
+        return s
+
+    for _ in range(5):
+        s = draw(s)
+    out = np.empty((n, 3))
+    for c in range(3):
+        s = draw(s)
+        out[:, c] = (1.0 / IM) * s
+    return out
+
+
+def create_velocities(sim, x, type_, temp=1.4, seed=87287):
+    """inputFile_impl.h:811-865: v = (u-0.5)/sqrt(m), subtract the global centre-of-mass
+    velocity, rescale to `temp` with T computed on the device (as the reference does)."""
+    m = sim.mass[type_]
+    u = velocity_geom_uniform(x, seed)
+    v = (u - 0.5) / np.sqrt(m)[:, None]
+    tot = np.array([m.sum(), (m * v[:, 0]).sum(), (m * v[:, 1]).sum(), (m * v[:, 2]).sum()])
+    if sim.nranks > 1:
+        tot = np.array([sim.ctx.reduce_sum(t) for t in tot])
+    v = v - tot[1:] / tot[0]
+    return v

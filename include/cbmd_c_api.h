@@ -144,6 +144,23 @@ extern "C"
     void *cbmd_stream( cbmd_ctx *ctx );
     /* number of kernels launched by this context since creation */
     int64_t cbmd_launch_count( cbmd_ctx *ctx );
+    /* CUDA-event timers around the module entry points, mirroring the reference's
+     * T_Force/T_Neigh/T_Comm/T_Int/T_Other buckets (cabanamd_impl.h:273-282,409-417),
+     * plus the LJ force kernel alone.  Off by default. */
+    enum
+    {
+        CBMD_T_FORCE = 0,        /* cbmd_zero_force + cbmd_force_lj            */
+        CBMD_T_NEIGH = 1,        /* cbmd_neigh_build                           */
+        CBMD_T_COMM = 2,         /* exchange / exchange_halo / update_*        */
+        CBMD_T_INTEGRATE = 3,    /* cbmd_integrate_initial / _final            */
+        CBMD_T_OTHER = 4,        /* cbmd_bin_sort, energy, sum_mv2             */
+        CBMD_T_FORCE_KERNEL = 5, /* the k_force_* launch only                  */
+        CBMD_T_NBUCKETS = 6
+    };
+    int cbmd_timing_enable( cbmd_ctx *ctx, int on );
+    /* synchronises, then returns accumulated milliseconds and region count */
+    int cbmd_timing_get( cbmd_ctx *ctx, int bucket, double *ms, int64_t *count );
+    int cbmd_timing_reset( cbmd_ctx *ctx );
     /* kernel variant switches for A/B measurements, e.g. "force_variant"=0|1 */
     int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value );
 
