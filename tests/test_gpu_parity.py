@@ -282,8 +282,10 @@ def test_trajectory_and_thermo_match_oracle(cb, half):
     tg, to = np.array(sim.thermo), np.array(s0.thermo())
     assert np.array_equal(tg[:, 0], to[:, 0])
     assert np.abs(tg[:, 1:] - to[:, 1:]).max() < 1e-9
-    # step-0 values are exact to round-off
-    assert np.abs(tg[0, 1:] - to[0, 1:]).max() < 1e-13
+    # step-0 values agree to summation-order round-off: the oracle adds ~2e5 pair
+    # energies sequentially into a sum of magnitude 2.5e4 (half-ulp 1.8e-12 per add),
+    # the GPU uses a two-level tree, so per-atom PE may differ by a few 1e-12
+    assert np.abs(tg[0, 1:] - to[0, 1:]).max() < 2e-11
     a, o = sim.ctx.get_atoms(), s0.get()
     assert np.array_equal(np.sort(a["id"][: a["n_local"]]), np.sort(o["id"][: o["n_local"]]))
     xa, _ = canon(a["x"][: a["n_local"]], a["id"][: a["n_local"]])
