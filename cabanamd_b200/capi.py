@@ -80,6 +80,7 @@ def load_library():
     L.cbmd_zero_force.argtypes = [vp]
     L.cbmd_force_lj.argtypes = [vp, C.c_int]
     L.cbmd_energy_lj.argtypes = [vp, C.c_int, c_dp, c_dp]
+    L.cbmd_request_energy.argtypes = [vp]
     L.cbmd_comm_unique_id.argtypes = [vp]
     L.cbmd_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.cbmd_comm_rank.argtypes = [vp, c_ip, c_ip]
@@ -278,6 +279,9 @@ class Context:
 
     def force(self, half=None):
         self._ck(self.L.cbmd_force_lj(self.h, int(self.half if half is None else half)))
+
+    def request_energy(self):
+        self._ck(self.L.cbmd_request_energy(self.h))
 
     def energy(self, half=None):
         a, b = C.c_double(), C.c_double()

@@ -276,6 +276,7 @@ extern "C" int cbmd_exchange( cbmd_ctx *ctx, int *n_sent_global )
     TimedRegion timed__( ctx, CBMD_T_COMM );
     CBMD_REQUIRE( ctx->have_domain, "cbmd_set_domain must be called before cbmd_exchange" );
     cbmd_materialize_zero_force( ctx );
+    ctx->epoch++;
     cudaStream_t s = ctx->stream;
     // system->resize(N_local): ghosts are dropped (comm_mpi_impl.h:196-197)
     ctx->n_ghost = 0;
@@ -426,6 +427,7 @@ extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
     CBMD_REQUIRE( ctx->have_domain, "cbmd_set_domain must be called before cbmd_exchange_halo" );
     CBMD_REQUIRE( comm_depth > 0, "comm depth must be positive" );
     cbmd_materialize_zero_force( ctx );
+    ctx->epoch++;
     cudaStream_t s = ctx->stream;
     ctx->comm_depth = comm_depth;
     ctx->n_ghost = 0;
@@ -578,6 +580,7 @@ extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
     CBMD_API_BEGIN
     TimedRegion timed__( ctx, CBMD_T_COMM );
     CBMD_REQUIRE( ctx->have_halo, "cbmd_exchange_halo must be called before cbmd_update_halo" );
+    ctx->epoch++;
     cudaStream_t s = ctx->stream;
     if ( ctx->n_ghost == 0 )
         return 0;

@@ -53,6 +53,7 @@ extern "C" int cbmd_integrate_initial( cbmd_ctx *ctx )
     CBMD_API_BEGIN
     TimedRegion timed__( ctx, CBMD_T_INTEGRATE );
     cbmd_materialize_zero_force( ctx );
+    ctx->epoch++;
     const int n = ctx->n_local;
     if ( n > 0 )
     {

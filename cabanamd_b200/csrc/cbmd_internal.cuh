@@ -31,6 +31,10 @@ struct LJTable
     double lj1[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
     double lj2[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
     double cutsq[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+    // pair-energy constants: e1 = 0.5*lj1/6, e2 = lj2/6, eshift = energy at the cutoff
+    double e1[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+    double e2[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+    double eshift[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
 };
 
 struct MassTable
@@ -75,6 +79,14 @@ struct cbmd_ctx
     int *id = nullptr, *id_alt = nullptr;
     double *q = nullptr, *q_alt = nullptr;
     bool f_zero_pending = false; // deferred deep_copy(f,0): fused into the full-list force kernel
+    // positions/list epoch: bumped by every call that moves atoms or rebuilds the list;
+    // validates the pair energy cached by a fused force+energy sweep
+    uint64_t epoch = 1;
+    bool energy_hint = false, pe_valid = false;
+    uint64_t pe_epoch = 0;
+    int pe_half = 0;
+    double *pe_partial = nullptr;
+    size_t pe_partial_cap = 0;
 
     // binning grid (binning_cabana.h:62-68) + cell lists over all atoms
     int nbin[3] = { 0, 0, 0 }, nhalo = 0;
@@ -270,6 +282,16 @@ __device__ __forceinline__ int cell_coord( double xv, double mn, double rdx, int
     c = c < 0 ? 0 : c;
     c = c > n - 1 ? n - 1 : c;
     return c;
+}
+
+// Verlet table layout: tiles of 32 consecutive atoms; neighbour n of atom i sits at
+//   nb[((i >> 5) * rows + n) * 32 + (i & 31)]
+// so a warp of 32 consecutive atoms reads row n as one 128-byte line (coalesced), and
+// everything a warp reads or writes lies in ONE contiguous rows*128-byte block (TLB- and
+// DRAM-page-local, unlike a [rows][n_atoms] table whose rows are megabytes apart).
+__host__ __device__ __forceinline__ size_t nb_tile_base( int i, int rows )
+{
+    return ( (size_t)( i >> 5 ) * (size_t)rows ) * 32 + (size_t)( i & 31 );
 }
 
 struct GridDesc

@@ -7,10 +7,11 @@
 // evaluated un-contracted, left to right); Full: i != j; Half: i != j and
 // (xj>xi || (xj==xi && (yj>yi || (yj==yi && zj>zi)))); ghost rows are empty.
 //
-// Device layout: padded, TRANSPOSED 2-D table — neighbour n of atom i lives at
-// nb[n * nb_stride + i] — so the thread-per-atom force kernel reads the index
-// stream fully coalesced.  The CSR view the reference also offers is produced on
-// demand by cbmd_neigh_get.  Row capacity follows Cabana's 2-D policy: start from
+// Device layout: padded 2-D table in tiles of 32 atoms — neighbour n of atom i lives
+// at nb[((i>>5)*rows + n)*32 + (i&31)] (nb_tile_base) — so the thread-per-atom force
+// kernel reads the index stream fully coalesced and each warp's rows are one
+// contiguous block.  The CSR view the reference also offers is produced on demand by
+// cbmd_neigh_get.  Row capacity follows Cabana's 2-D policy: start from
 // max_neigh_guess, and if any row overflows rebuild at 1.1 x the observed maximum.
 #include "cbmd_internal.cuh"
 
@@ -23,65 +24,275 @@ __device__ __forceinline__ bool half_valid( const XT &a, const XT &b )
     return b.x > a.x || ( b.x == a.x && ( b.y > a.y || ( b.y == a.y && b.z > a.z ) ) );
 }
 
-// one warp per owned atom; lanes sweep the candidates of the 27-cell stencil, nine
-// runs that are contiguous in cell_atoms (z is the fastest cell index).
+// ---------------------------------------------------------------------------
+// k_neigh_build: one CTA per NBC z-consecutive cells of one (x,y) column of the Verlet
+// grid, one warp per cell, one LANE per owned atom of that cell.
+//
+//  1. The 27-cell stencils of the CTA's cells are together at most nine runs that are
+//     contiguous in cell_atoms (z is the fastest cell index).  The CTA stages the
+//     candidates of those runs once in shared memory as 16-byte records
+//     {x,y,z relative to the column block centre as FP32, atom index}.
+//  2. Each warp walks the candidates of its own cell's stencil (nine sub-segments of
+//     the staged runs); the record is a shared-memory BROADCAST read, and every lane
+//     tests it against its own atom, so no cross-lane compaction is needed: a lane
+//     appends straight to its row of the transposed table.
+//  3. d^2 <= r^2 is decided in FP32 only when that is provably equal to the exact
+//     answer: with tol0 bounding the relative FP32 error (> 10x the worst case) the
+//     candidate is "surely inside" below r2lo = (r2-tol0)/(1+tol0) and "surely outside"
+//     above r2hi = (r2+tol0)/(1-tol0); anything in between is re-evaluated with the
+//     reference's exact FP64 expression (un-contracted, left to right) from the global
+//     positions, so the SET is bit-identical to the oracle's.  The half-list
+//     discriminator (xj > xi, ties by y, z) gets the same treatment.
+// Stencils larger than the staging buffer are processed in chunks; per-lane counts
+// live in registers across chunks.  Rows are in ascending (cell, index) order.
+// ---------------------------------------------------------------------------
+// K staged candidates against this lane's atom: FP32 decisions, ONE warp vote for the
+// (rare) exact FP64 re-evaluation, then in-order appends to the lane's row.
+template <bool HALF, int K>
+__device__ __forceinline__ void
+sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const XT &xi, float xr,
+             float yr, float zr, int i, bool active, float r2lo, float r2hi, float tolx,
+             double rsqr, char *row0, unsigned row_bytes, int nb_rows, int &count )
+{
+    float4 c[K];
+#pragma unroll
+    for ( int k = 0; k < K; k++ )
+        c[k] = cand[k];
+    bool ok[K], amb[K];
+    bool any_amb = false;
+#pragma unroll
+    for ( int k = 0; k < K; k++ )
+    {
+        const float fx = c[k].x - xr, fy = c[k].y - yr, fz = c[k].z - zr;
+        const float d2 = fx * fx + fy * fy + fz * fz;
+        const bool ns = active && ( __float_as_int( c[k].w ) != i );
+        ok[k] = ns && ( d2 < r2lo );
+        amb[k] = ns && ( d2 < r2hi );
+        if ( HALF )
+        {
+            // xj > xi decided in FP32 unless |xj - xi| is within its error
+            ok[k] = ok[k] && ( fx > tolx );
+            amb[k] = amb[k] && ( fx >= -tolx );
+        }
+        amb[k] = amb[k] && !ok[k];
+        any_amb = any_amb || amb[k];
+    }
+    if ( __any_sync( 0xffffffffu, any_amb ) )
+    {
+#pragma unroll
+        for ( int k = 0; k < K; k++ )
+            if ( amb[k] )
+            { // exact re-evaluation of the reference criterion (rare)
+                const XT xj = ld_xt( xt + __float_as_int( c[k].w ) );
+                ok[k] = dist2_exact( __dsub_rn( xi.x, xj.x ), __dsub_rn( xi.y, xj.y ),
+                                     __dsub_rn( xi.z, xj.z ) ) <= rsqr;
+                if ( HALF )
+                    ok[k] = ok[k] && half_valid( xi, xj );
+            }
+    }
+#pragma unroll
+    for ( int k = 0; k < K; k++ )
+        if ( ok[k] )
+        {
+            if ( count < nb_rows )
+                *(int *)( row0 + (unsigned long long)(unsigned)count * row_bytes ) =
+                    __float_as_int( c[k].w );
+            count++;
+        }
+}
+
+#define NBC 4
+#define NB_THREADS ( 32 * NBC )
+#define NB_STAGE 1280 // candidates per staging chunk (20 KB)
+
 template <bool HALF>
-__global__ void __launch_bounds__( 256 )
+__global__ void __launch_bounds__( NB_THREADS )
     k_neigh_build( const XT *__restrict__ xt, int n_local, GridDesc g,
                    const int *__restrict__ cell_start, const int *__restrict__ cell_atoms,
-                   double rsqr, int *__restrict__ nb, int nb_stride, int nb_rows,
+                   double rsqr, double3 centre, int *__restrict__ nb, int nb_stride, int nb_rows,
                    int *__restrict__ nb_count, int *__restrict__ d_max )
 {
-    const int i = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
-    const int lane = threadIdx.x & 31;
-    if ( i >= n_local )
+    __shared__ float4 cand[NB_STAGE];
+    __shared__ int run_src[9], run_off[10];
+    __shared__ int s_mag;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nz = g.n[2], nzb = ( nz + NBC - 1 ) / NBC;
+    const int col = blockIdx.x / nzb, c0 = ( blockIdx.x - col * nzb ) * NBC;
+    const int ca = col / g.n[1], cb = col - ca * g.n[1];
+    const int c1 = min( c0 + NBC, nz ) - 1; // last cell of this block
+    const int colrow = ( ca * g.n[1] + cb ) * nz;
+
+    // this warp's cell and its owned atoms (owned atoms come first inside a cell:
+    // ascending index, ghosts have index >= n_local)
+    const int cc = c0 + warp;
+    int cs = 0, ce = 0;
+    if ( cc <= c1 )
+    {
+        cs = cell_start[colrow + cc];
+        ce = cell_start[colrow + cc + 1];
+    }
+    const bool has_owned = ( ce > cs ) && ( cell_atoms[cs] < n_local );
+    if ( !__syncthreads_or( has_owned ) )
         return;
-    const XT xi = ld_xt( xt + i );
-    const int ca = cell_coord( xi.x, g.mn[0], g.rdx[0], g.n[0] );
-    const int cb = cell_coord( xi.y, g.mn[1], g.rdx[1], g.n[1] );
-    const int cc = cell_coord( xi.z, g.mn[2], g.rdx[2], g.n[2] );
-    const int c_lo = max( cc - 1, 0 ), c_hi = min( cc + 1, g.n[2] - 1 );
-    const unsigned lt_mask = ( 1u << lane ) - 1u;
-    int count = 0;
-    for ( int a = max( ca - 1, 0 ); a <= min( ca + 1, g.n[0] - 1 ); a++ )
-        for ( int b = max( cb - 1, 0 ); b <= min( cb + 1, g.n[1] - 1 ); b++ )
+
+    // nine runs (x,y neighbours of the column) x cells [c0-1, c1+1]
+    const int zlo = max( c0 - 1, 0 ), zhi = min( c1 + 1, nz - 1 );
+    int seg_b = 0, seg_e = 0; // lane r < 9: this warp's sub-segment of run r (staged coords)
+    {
+        int s0 = 0, len = 0, w0 = 0, w1 = 0;
+        if ( lane < 9 )
         {
-            const int row = ( a * g.n[1] + b ) * g.n[2];
-            const int s0 = cell_start[row + c_lo], s1 = cell_start[row + c_hi + 1];
-            for ( int base = s0; base < s1; base += 32 )
+            const int a = ca + lane / 3 - 1, b = cb + lane % 3 - 1;
+            if ( a >= 0 && a < g.n[0] && b >= 0 && b < g.n[1] )
             {
-                const int s = base + lane;
-                bool ok = false;
-                int j = -1;
-                if ( s < s1 )
+                const int row = ( a * g.n[1] + b ) * nz;
+                s0 = cell_start[row + zlo];
+                len = cell_start[row + zhi + 1] - s0;
+                if ( cc <= c1 )
                 {
-                    j = cell_atoms[s];
-                    const XT xj = ld_xt( xt + j );
-                    const double d2 = dist2_exact( __dsub_rn( xi.x, xj.x ), __dsub_rn( xi.y, xj.y ),
-                                                   __dsub_rn( xi.z, xj.z ) );
-                    ok = ( j != i ) && ( d2 <= rsqr );
-                    if ( HALF )
-                        ok = ok && half_valid( xi, xj );
+                    w0 = cell_start[row + max( cc - 1, 0 )] - s0;
+                    w1 = cell_start[row + min( cc + 1, nz - 1 ) + 1] - s0;
                 }
-                const unsigned m = __ballot_sync( 0xffffffffu, ok );
-                if ( ok )
-                {
-                    const int p = count + __popc( m & lt_mask );
-                    if ( p < nb_rows )
-                        nb[(size_t)p * nb_stride + i] = j;
-                }
-                count += __popc( m );
             }
         }
-    if ( lane == 0 )
+        int off = len; // inclusive scan over lanes 0..8
+        for ( int o = 1; o < 16; o <<= 1 )
+        {
+            const int v = __shfl_up_sync( 0xffffffffu, off, o );
+            if ( lane >= o )
+                off += v;
+        }
+        off -= len; // exclusive
+        seg_b = off + w0;
+        seg_e = off + w1;
+        if ( warp == 0 )
+        {
+            if ( lane < 9 )
+            {
+                run_src[lane] = s0;
+                run_off[lane] = off;
+            }
+            if ( lane == 9 )
+                run_off[9] = off; // == total (len is 0 for lanes >= 9)
+            if ( lane == 0 )
+                s_mag = 0;
+        }
+    }
+    __syncthreads();
+    const int total = run_off[9];
+
+    // origin of the FP32 relative coordinates: centre of this block of cells
+    const double ox = g.rdx[0] > 0.0 ? g.mn[0] + ( ca + 0.5 ) / g.rdx[0] : centre.x;
+    const double oy = g.rdx[1] > 0.0 ? g.mn[1] + ( cb + 0.5 ) / g.rdx[1] : centre.y;
+    const double oz = g.rdx[2] > 0.0 ? g.mn[2] + ( 0.5 * ( c0 + c1 ) + 0.5 ) / g.rdx[2] : centre.z;
+    const float r2f = (float)rsqr;
+    const unsigned row_bytes = 128u; // 32 atoms x 4 bytes per row of a tile
+
+    // passes of 32 atoms of each warp's cell (one pass unless a cell is crowded); the
+    // pass and chunk loops are CTA-uniform because staging needs block barriers
+    __shared__ int s_npass;
+    if ( threadIdx.x == 0 )
+        s_npass = 1;
+    __syncthreads();
+    if ( lane == 0 && ce - cs > 32 )
+        atomicMax( &s_npass, ( ce - cs + 31 ) >> 5 );
+    __syncthreads();
+    const int n_pass = s_npass;
+    const bool multi_chunk = total > NB_STAGE;
+
+    for ( int pass = 0; pass < n_pass; pass++ )
     {
-        nb_count[i] = count;
-        atomicMax( d_max, count );
+        const int s = cs + pass * 32 + lane;
+        int i = -1;
+        if ( s < ce )
+        {
+            i = cell_atoms[s];
+            if ( i >= n_local )
+                i = -1;
+        }
+        const bool active = i >= 0;
+        const bool any_active = __any_sync( 0xffffffffu, active );
+        XT xi;
+        xi.x = xi.y = xi.z = 0.0;
+        xi.t = 0;
+        if ( active )
+            xi = ld_xt( xt + i );
+        const float xr = active ? (float)( xi.x - ox ) : 0.f, yr = active ? (float)( xi.y - oy ) : 0.f,
+                    zr = active ? (float)( xi.z - oz ) : 0.f;
+        char *const row0 = (char *)( nb + nb_tile_base( active ? i : 0, nb_rows ) );
+        int count = 0;
+
+        for ( int chunk = 0; chunk < total; chunk += NB_STAGE )
+        {
+            const int nstage = min( NB_STAGE, total - chunk );
+            // ---- stage [chunk, chunk + nstage) of the concatenated runs; a single chunk
+            //      is staged once and stays valid for later passes
+            if ( multi_chunk || pass == 0 )
+            {
+                if ( multi_chunk && ( chunk > 0 || pass > 0 ) )
+                    __syncthreads(); // everyone is done with the previous contents
+                float mag = 0.f;
+                for ( int t = threadIdx.x; t < nstage; t += NB_THREADS )
+                {
+                    const int q = chunk + t;
+                    int r = 0;
+#pragma unroll
+                    for ( int k = 1; k < 9; k++ )
+                        r += ( q >= run_off[k] );
+                    const int j = cell_atoms[run_src[r] + ( q - run_off[r] )];
+                    const XT xj = ld_xt( xt + j );
+                    const float4 c = make_float4( (float)( xj.x - ox ), (float)( xj.y - oy ),
+                                                  (float)( xj.z - oz ), __int_as_float( j ) );
+                    mag = fmaxf( mag, fmaxf( fabsf( c.x ), fmaxf( fabsf( c.y ), fabsf( c.z ) ) ) );
+                    cand[t] = c;
+                }
+                // largest |relative coordinate| staged so far (non-negative floats order like ints)
+                for ( int o = 16; o > 0; o >>= 1 )
+                    mag = fmaxf( mag, __shfl_xor_sync( 0xffffffffu, mag, o ) );
+                if ( lane == 0 )
+                    atomicMax( &s_mag, __float_as_int( mag ) );
+                __syncthreads();
+            }
+            if ( !any_active )
+                continue;
+            // FP32 error of d2: relative coordinates carry <= 2^-24*M each (M = largest
+            // magnitude), so |fx - dx| <= 2.4e-7*M and, with three more roundings in the
+            // sum, |d2f - d2| <= (8.4e-7*M + 1.8e-7)*(1 + d2).  tol0 is > 10x that.
+            float M = fmaxf( fabsf( xr ), fmaxf( fabsf( yr ), fabsf( zr ) ) );
+            for ( int o = 16; o > 0; o >>= 1 )
+                M = fmaxf( M, __shfl_xor_sync( 0xffffffffu, M, o ) );
+            M = fmaxf( M, __int_as_float( s_mag ) );
+            const float tol0 = 4.0e-6f + 1.0e-5f * M;
+            const float r2lo = ( r2f - tol0 ) / ( 1.0f + tol0 ) * 0.999999f;
+            const float r2hi = ( r2f + tol0 ) / ( 1.0f - tol0 ) * 1.000001f;
+            const float tolx = 1.0e-5f * fmaxf( 1.0f, M );
+#pragma unroll 1
+            for ( int r = 0; r < 9; r++ )
+            {
+                const int b = max( __shfl_sync( 0xffffffffu, seg_b, r ) - chunk, 0 );
+                const int e = min( __shfl_sync( 0xffffffffu, seg_e, r ) - chunk, nstage );
+                int t = b;
+                for ( ; t + 4 <= e; t += 4 )
+                    sweep_group<HALF, 4>( cand + t, xt, xi, xr, yr, zr, i, active, r2lo, r2hi, tolx,
+                                          rsqr, row0, row_bytes, nb_rows, count );
+                for ( ; t < e; t++ )
+                    sweep_group<HALF, 1>( cand + t, xt, xi, xr, yr, zr, i, active, r2lo, r2hi, tolx,
+                                          rsqr, row0, row_bytes, nb_rows, count );
+            }
+        }
+        if ( active )
+            nb_count[i] = count;
+        int mx = count;
+        for ( int o = 16; o > 0; o >>= 1 )
+            mx = max( mx, __shfl_xor_sync( 0xffffffffu, mx, o ) );
+        if ( lane == 0 && mx > 0 )
+            atomicMax( d_max, mx );
     }
 }
 
 __global__ void __launch_bounds__( 256 )
-    k_nb_to_csr( const int *__restrict__ nb, int nb_stride, const int *__restrict__ nb_count,
+    k_nb_to_csr( const int *__restrict__ nb, int nb_rows, const int *__restrict__ nb_count,
                  const int64_t *__restrict__ offsets, int n_local, int *__restrict__ csr )
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,7 +301,7 @@ __global__ void __launch_bounds__( 256 )
     const int c = nb_count[i];
     const int64_t o = offsets[i];
     for ( int n = 0; n < c; n++ )
-        csr[o + n] = nb[(size_t)n * nb_stride + i];
+        csr[o + n] = nb[nb_tile_base( i, nb_rows ) + (size_t)n * 32];
 }
 
 extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layout,
@@ -103,6 +314,7 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
     CBMD_REQUIRE( layout == CBMD_LAYOUT_2D || layout == CBMD_LAYOUT_CSR, "unknown list layout" );
     const int n_local = ctx->n_local, n_total = ctx->n_local + ctx->n_ghost;
     cudaStream_t s = ctx->stream;
+    ctx->epoch++;
 
     // cell grid of size >= rcut around the owned box; atoms outside are clamped into
     // the edge cells, which keeps |cell(i)-cell(j)| <= 1 for every pair within rcut.
@@ -128,6 +340,9 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
     int rows = max_neigh_guess > 0 ? max_neigh_guess : 1;
     const int stride = ( n_local + 31 ) & ~31;
     const double rsqr = rcut * rcut;
+    const double3 centre = make_double3( 0.5 * ( ctx->llo[0] + ctx->lhi[0] ),
+                                         0.5 * ( ctx->llo[1] + ctx->lhi[1] ),
+                                         0.5 * ( ctx->llo[2] + ctx->lhi[2] ) );
     int *d_max = ctx->d_flags;
     if ( n_total > 0 )
         CBMD_CUDA( cudaMemsetAsync( ctx->nb_count, 0, (size_t)n_total * sizeof( int ), s ) );
@@ -151,15 +366,15 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
         CBMD_CUDA( cudaMemsetAsync( d_max, 0, sizeof( int ), s ) );
         if ( n_local > 0 )
         {
-            const int blocks = (int)div_up64( (int64_t)n_local * 32, 256 );
+            const int blocks = g.n[0] * g.n[1] * ( ( g.n[2] + NBC - 1 ) / NBC );
             if ( half )
-                k_neigh_build<true><<<blocks, 256, 0, s>>>( ctx->xt, n_local, g, ctx->cell_start,
-                                                            ctx->cell_atoms, rsqr, ctx->nb, stride,
-                                                            rows, ctx->nb_count, d_max );
+                k_neigh_build<true><<<blocks, NB_THREADS, 0, s>>>(
+                    ctx->xt, n_local, g, ctx->cell_start, ctx->cell_atoms, rsqr, centre, ctx->nb,
+                    stride, rows, ctx->nb_count, d_max );
             else
-                k_neigh_build<false><<<blocks, 256, 0, s>>>( ctx->xt, n_local, g, ctx->cell_start,
-                                                             ctx->cell_atoms, rsqr, ctx->nb,
-                                                             stride, rows, ctx->nb_count, d_max );
+                k_neigh_build<false><<<blocks, NB_THREADS, 0, s>>>(
+                    ctx->xt, n_local, g, ctx->cell_start, ctx->cell_atoms, rsqr, centre, ctx->nb,
+                    stride, rows, ctx->nb_count, d_max );
             CBMD_LAUNCH_CHECK( ctx );
         }
         // NeighborList<>::maxNeighbor (neighbor_verlet.h:58-59)
@@ -213,7 +428,7 @@ extern "C" int cbmd_neigh_get( cbmd_ctx *ctx, int *counts, int64_t *offsets, int
         int *d_csr = (int *)( st + ob );
         CBMD_CUDA( cudaMemcpyAsync( d_off, ho.data(), (size_t)( n_local + 1 ) * sizeof( int64_t ),
                                     cudaMemcpyHostToDevice, s ) );
-        k_nb_to_csr<<<div_up( n_local, 256 ), 256, 0, s>>>( ctx->nb, ctx->nb_stride, ctx->nb_count,
+        k_nb_to_csr<<<div_up( n_local, 256 ), 256, 0, s>>>( ctx->nb, ctx->nb_rows, ctx->nb_count,
                                                             d_off, n_local, d_csr );
         CBMD_LAUNCH_CHECK( ctx );
         CBMD_CUDA( cudaMemcpyAsync( neighbors, d_csr, (size_t)ho[n_local] * sizeof( int ),

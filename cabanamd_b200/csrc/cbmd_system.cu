@@ -246,7 +246,8 @@ extern "C" int cbmd_destroy( cbmd_ctx *ctx )
                      ctx->q,          ctx->q_alt,       ctx->cell_start, ctx->cell_cursor,
                      ctx->cell_atoms, ctx->atom_cell,   ctx->perm,       ctx->nb,
                      ctx->nb_count,   ctx->ghost_owner, ctx->ghost_image, ctx->sendbuf,
-                     ctx->recvbuf,    ctx->scratch,     ctx->d_red,      ctx->d_flags };
+                     ctx->recvbuf,    ctx->scratch,     ctx->d_red,      ctx->d_flags,
+                     ctx->pe_partial };
     for ( void *p : ptrs )
         if ( p )
             cudaFree( p );
@@ -457,6 +458,7 @@ extern "C" int cbmd_set_atoms( cbmd_ctx *ctx, int n_local, const double *x, cons
     CBMD_REQUIRE( n_local >= 0, "negative atom count" );
     ctx->n_local = 0;
     ctx->n_ghost = 0;
+    ctx->epoch++;
     cbmd_ensure_capacity( ctx, n_local );
     ctx->f_zero_pending = false;
     upload_rows( ctx, 0, n_local, x, v, f, type, id, q, 1 );
@@ -473,6 +475,7 @@ extern "C" int cbmd_append_ghosts( cbmd_ctx *ctx, int n, const double *x, const 
     CBMD_API_BEGIN
     CBMD_REQUIRE( n >= 0, "negative ghost count" );
     cbmd_materialize_zero_force( ctx );
+    ctx->epoch++;
     const int first = ctx->n_local + ctx->n_ghost;
     cbmd_ensure_capacity( ctx, first + n );
     upload_rows( ctx, first, n, x, nullptr, nullptr, type, id, nullptr, first + 1 );

@@ -49,6 +49,7 @@ class Simulation:
         self.step = 0
         self.N = 0
         self.thermo = []
+        self.fuse_energy = True
 
     def set_box(self, glo, ghi):
         d = make_domain(glo, ghi, self.nranks, self.rank, self.ghost_cutoff)
@@ -98,6 +99,8 @@ class Simulation:
             else:
                 c.update_halo()
             c.zero_force()
+            if thermo_rate and self.step % thermo_rate == 0 and self.fuse_energy:
+                c.request_energy()  # thermo step: PE in the same sweep as the force
             c.force(self.half)
             if self.half:
                 c.update_force()

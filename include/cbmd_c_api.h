@@ -111,6 +111,12 @@ extern "C"
      * pe_corrected (may be NULL): half-list energy with fac=1 for every stored pair
      * (SURVEY Appendix B.4); equals *pe for full lists. */
     int cbmd_energy_lj( cbmd_ctx *ctx, int half, double *pe, double *pe_corrected );
+    /* One-shot hint from the step loop (cabanamd_impl.h:363-366 evaluates the energy on
+     * thermo steps right after force->compute at unchanged positions): the NEXT
+     * cbmd_force_lj also accumulates compute_energy in the same neighbour sweep, and
+     * the following cbmd_energy_lj returns that value provided no call moved atoms or
+     * rebuilt the list in between (otherwise it runs its own sweep, as without the hint). */
+    int cbmd_request_energy( cbmd_ctx *ctx );
 
     /* ---- Comm (comm_mpi.h:125-138, comm_mpi_impl.h) ----------------------------- */
     /* 128-byte NCCL unique id created on rank 0 and handed to every rank out of band */

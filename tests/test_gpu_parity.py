@@ -341,3 +341,111 @@ def test_newton3_properties_full_size(cb):
     assert np.abs(out[False].sum(axis=0)).max() < 1e-9 * scale * 1000
     assert np.abs(out[False] - out[True]).max() < 1e-10 * scale
     assert out[("tot", False)] == 2 * out[("tot", True)]
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_fused_energy_matches_standalone(cb, half):
+    """cbmd_request_energy: the PE accumulated inside the force sweep equals the
+    stand-alone compute_energy sweep, and the cache is dropped as soon as atoms move."""
+    s = melted_state((8, 8, 8), 40, half)
+    d = s.get()
+    n, ng = d["n_local"], d["n_ghost"]
+    dom = s.domain()
+    lj1, lj2, cutsq = s.tables
+    ctx = cb.Context(0)
+    ctx.set_mass([2.0])
+    ctx.set_lj(lj1, lj2, cutsq)
+    ctx.set_domain(dom["llo"], dom["lhi"])
+    ctx.set_atoms(d["x"][:n], d["v"][:n], None, d["type"][:n], d["id"][:n])
+    ctx.append_ghosts(d["x"][n:], d["type"][n:], d["id"][n:])
+    ctx.neigh_build(2.8, half, 0, 90)
+    ctx.zero_force()
+    ctx.force(half)
+    f_plain = ctx.get_atoms()["f"]
+    pe0, pec0 = ctx.energy(half)           # stand-alone sweep
+    l0 = ctx.launch_count()
+    ctx.zero_force()
+    ctx.request_energy()
+    ctx.force(half)
+    l1 = ctx.launch_count()
+    pe1, pec1 = ctx.energy(half)           # served from the fused sweep: no new kernel
+    assert ctx.launch_count() == l1 and l1 > l0
+    assert abs(pe1 - pe0) <= 1e-13 * abs(pe0) and abs(pec1 - pec0) <= 1e-13 * abs(pec0)
+    f_fused = ctx.get_atoms()["f"]
+    if not half:  # half-list forces go through FP64 atomics: order-dependent last bits
+        assert np.array_equal(f_fused, f_plain)
+    else:
+        assert np.abs(f_fused - f_plain).max() <= 1e-12 * np.abs(f_plain).max()
+    e_ref = O.NeighList().set(n, n + ng, *s.list()).energy(d["x"], d["type"], half, lj1, lj2, cutsq)
+    assert abs(pe1 - e_ref) <= 1e-12 * abs(e_ref)
+    # the hint is one-shot and the cache dies when positions change
+    ctx.integrate_initial()
+    l2 = ctx.launch_count()
+    ctx.energy(half)
+    assert ctx.launch_count() > l2
+
+
+def test_neighbor_build_hard_cases(cb):
+    """Cases aimed at the staged / FP32-prefiltered build: (a) a dense blob whose
+    27-cell stencil exceeds one staging chunk, (b) pairs within 1e-12 of the cutoff on
+    both sides (FP32-ambiguous -> exact FP64 fallback), (c) a perfect lattice (equal-x
+    ties for the half discriminator), (d) a box thinner than the cutoff."""
+    rng = np.random.default_rng(77)
+    # (a) 3000 atoms inside a 3x3x3 sigma blob + 500 spread out; rc 1.0
+    blob = rng.uniform(4.0, 7.0, size=(3000, 3))
+    rest = rng.uniform(0.0, 12.0, size=(500, 3))
+    x = np.concatenate([blob, rest])
+    for half in (False, True):
+        ctx = cb.Context(0)
+        ctx.set_domain([0.0] * 3, [12.0] * 3)
+        ctx.set_atoms(x[:3200])
+        ctx.append_ghosts(x[3200:])
+        ctx.neigh_build(1.0, half, 0, 64)
+        ref = O.NeighList().brute(x, 3200, 1.0, half)
+        counts, rows = gpu_rows(ctx)
+        assert np.array_equal(counts, ref.arrays()[0])
+        for a, b in zip(rows, ref.rows_sorted()):
+            assert np.array_equal(a, b)
+    # (b) shells of partners at r = rc*(1 +- k*2^-50) around random centres
+    rc = 2.5
+    centres = rng.uniform(3.0, 17.0, size=(40, 3))
+    pts = [centres]
+    for k in range(-6, 7):
+        u = rng.normal(size=(40, 3))
+        u /= np.linalg.norm(u, axis=1)[:, None]
+        pts.append(centres + u * rc * (1.0 + k * 2.0 ** -50))
+    x = np.concatenate(pts)
+    for half in (False, True):
+        ctx = cb.Context(0)
+        ctx.set_domain([0.0] * 3, [20.0] * 3)
+        ctx.set_atoms(x)
+        ctx.neigh_build(rc, half, 1, 8)
+        ref = O.NeighList().brute(x, len(x), rc, half)
+        counts, rows = gpu_rows(ctx)
+        assert np.array_equal(counts, ref.arrays()[0])
+        for a, b in zip(rows, ref.rows_sorted()):
+            assert np.array_equal(a, b)
+    # (c) perfect sc lattice, spacing 1.0, rc exactly sqrt(2) -> many d^2 == rc^2 and x ties
+    g = np.arange(8, dtype=np.float64)
+    x = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3) + 0.5
+    for half in (False, True):
+        ctx = cb.Context(0)
+        ctx.set_domain([0.0] * 3, [8.0] * 3)
+        ctx.set_atoms(x)
+        ctx.neigh_build(np.sqrt(2.0), half, 0, 20)
+        ref = O.NeighList().brute(x, len(x), np.sqrt(2.0), half)
+        counts, rows = gpu_rows(ctx)
+        assert np.array_equal(counts, ref.arrays()[0])
+        for a, b in zip(rows, ref.rows_sorted()):
+            assert np.array_equal(a, b)
+    # (d) slab: z extent 1.5 < rc 2.8, long in x
+    x = rng.uniform([0, 0, 0], [300.0, 9.0, 1.5], size=(4000, 3))
+    ctx = cb.Context(0)
+    ctx.set_domain([0.0] * 3, [300.0, 9.0, 1.5])
+    ctx.set_atoms(x)
+    ctx.neigh_build(2.8, False, 0, 40)
+    ref = O.NeighList().brute(x, len(x), 2.8, False)
+    counts, rows = gpu_rows(ctx)
+    assert np.array_equal(counts, ref.arrays()[0])
+    for a, b in zip(rows, ref.rows_sorted()):
+        assert np.array_equal(a, b)
