@@ -47,13 +47,14 @@ __device__ __forceinline__ bool half_valid( const XT &a, const XT &b )
 // live in registers across chunks.  Rows are in ascending (cell, index) order.
 // ---------------------------------------------------------------------------
 // K staged candidates against this lane's atom: FP32 decisions, ONE warp vote for the
-// (rare) exact FP64 re-evaluation, then in-order appends to the lane's row.
+// (rare) exact FP64 re-evaluation, then in-order, branch-free appends to the lane's row.
 template <bool HALF, int K>
 __device__ __forceinline__ void
 sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const XT &xi, float xr,
-             float yr, float zr, int i, bool active, float r2lo, float r2hi, float tolx,
-             double rsqr, char *row0, unsigned row_bytes, int nb_rows, int &count )
+             float yr, float zr, int i, float r2lo, float r2hi, float tolx, double rsqr,
+             char *row0, int nb_rows, int &count )
 {
+    // i < 0 marks an inactive lane: its r2lo/r2hi are -1 so nothing is ever accepted
     float4 c[K];
 #pragma unroll
     for ( int k = 0; k < K; k++ )
@@ -65,7 +66,7 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
     {
         const float fx = c[k].x - xr, fy = c[k].y - yr, fz = c[k].z - zr;
         const float d2 = fx * fx + fy * fy + fz * fz;
-        const bool ns = active && ( __float_as_int( c[k].w ) != i );
+        const bool ns = __float_as_int( c[k].w ) != i;
         ok[k] = ns && ( d2 < r2lo );
         amb[k] = ns && ( d2 < r2hi );
         if ( HALF )
@@ -92,13 +93,16 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
     }
 #pragma unroll
     for ( int k = 0; k < K; k++ )
-        if ( ok[k] )
-        {
-            if ( count < nb_rows )
-                *(int *)( row0 + (unsigned long long)(unsigned)count * row_bytes ) =
-                    __float_as_int( c[k].w );
-            count++;
-        }
+    {
+        // predicated store (no branch): row n of this lane's column is 128 bytes further on
+        const int st = ( ok[k] && count < nb_rows ) ? 1 : 0;
+        char *dst = row0 + (unsigned long long)(unsigned)count * 128ull;
+        asm volatile( "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b32 [%0], %1;\n\t}"
+                      :
+                      : "l"( dst ), "r"( __float_as_int( c[k].w ) ), "r"( st )
+                      : "memory" );
+        count += ok[k] ? 1 : 0;
+    }
 }
 
 #define NBC 4
@@ -187,7 +191,6 @@ __global__ void __launch_bounds__( NB_THREADS )
     const double oy = g.rdx[1] > 0.0 ? g.mn[1] + ( cb + 0.5 ) / g.rdx[1] : centre.y;
     const double oz = g.rdx[2] > 0.0 ? g.mn[2] + ( 0.5 * ( c0 + c1 ) + 0.5 ) / g.rdx[2] : centre.z;
     const float r2f = (float)rsqr;
-    const unsigned row_bytes = 128u; // 32 atoms x 4 bytes per row of a tile
 
     // passes of 32 atoms of each warp's cell (one pass unless a cell is crowded); the
     // pass and chunk loops are CTA-uniform because staging needs block barriers
@@ -267,18 +270,21 @@ __global__ void __launch_bounds__( NB_THREADS )
             const float r2lo = ( r2f - tol0 ) / ( 1.0f + tol0 ) * 0.999999f;
             const float r2hi = ( r2f + tol0 ) / ( 1.0f - tol0 ) * 1.000001f;
             const float tolx = 1.0e-5f * fmaxf( 1.0f, M );
+            // inactive lanes accept nothing
+            const float r2lo_l = active ? r2lo : -1.0f, r2hi_l = active ? r2hi : -1.0f;
 #pragma unroll 1
             for ( int r = 0; r < 9; r++ )
             {
                 const int b = max( __shfl_sync( 0xffffffffu, seg_b, r ) - chunk, 0 );
-                const int e = min( __shfl_sync( 0xffffffffu, seg_e, r ) - chunk, nstage );
-                int t = b;
-                for ( ; t + 4 <= e; t += 4 )
-                    sweep_group<HALF, 4>( cand + t, xt, xi, xr, yr, zr, i, active, r2lo, r2hi, tolx,
-                                          rsqr, row0, row_bytes, nb_rows, count );
-                for ( ; t < e; t++ )
-                    sweep_group<HALF, 1>( cand + t, xt, xi, xr, yr, zr, i, active, r2lo, r2hi, tolx,
-                                          rsqr, row0, row_bytes, nb_rows, count );
+                const int e = max( min( __shfl_sync( 0xffffffffu, seg_e, r ) - chunk, nstage ), b );
+                const int n4 = ( e - b ) >> 2;
+                const float4 *cp = cand + b;
+                for ( int q = 0; q < n4; q++, cp += 4 )
+                    sweep_group<HALF, 4>( cp, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx, rsqr, row0,
+                                          nb_rows, count );
+                for ( int t = b + 4 * n4; t < e; t++ )
+                    sweep_group<HALF, 1>( cand + t, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx, rsqr,
+                                          row0, nb_rows, count );
             }
         }
         if ( active )
