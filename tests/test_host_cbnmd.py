@@ -1,0 +1,167 @@
+"""The C++ host layer (cabanamd_b200/host: reference class surface + cbnMD driver).
+
+CPU tests: the driver builds, parses decks with the reference's error convention, and
+fails loudly without a GPU.  GPU tests: `cbnMD -il <deck>` reproduces the oracle's thermo
+trace and the reference's output layout."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CBNMD = os.path.join(ROOT, "cabanamd_b200", "lib", "cbnMD")
+
+DECK = """# 3d Lennard-Jones melt
+units           lj
+atom_style      atomic
+
+newton          off
+lattice         fcc 0.8442
+region          box block 0 {c} 0 {c} 0 {c}
+create_box      1 box
+create_atoms    1 box
+mass            1 2.0
+
+velocity        all create 1.4 87287 loop geom
+
+pair_style      lj/cut 2.5
+pair_coeff      1 1 1.0 1.0 2.5
+
+neighbor        0.3 bin
+neigh_modify    every 20 one 50
+comm_modify     cutoff * 20
+fix             1 all nve
+thermo          10
+
+dump            dmpvtk all vtk 10 dump%_*.vtu
+
+run             {steps}
+"""
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "cabanamd_b200", "csrc")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "cabanamd_b200", "host")])
+    assert os.path.exists(CBNMD)
+
+
+def run_cbnmd(tmp_path, deck, *args, env=None):
+    f = tmp_path / "in.deck"
+    f.write_text(deck)
+    out, err = tmp_path / "md.out", tmp_path / "md.err"
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([CBNMD, "-il", str(f), "-o", str(out), "-e", str(err), *args],
+                       capture_output=True, text=True, cwd=tmp_path, env=e, timeout=600)
+    return p, (out.read_text() if out.exists() else ""), (err.read_text() if err.exists() else "")
+
+
+def test_unknown_keyword_is_an_input_error(tmp_path):
+    p, out, err = run_cbnmd(tmp_path, "units lj\nfoo bar\n")
+    assert p.returncode != 0
+    assert "Unknown input file keyword: foo bar" in err
+    assert "Aborting after error from input. See error file." in p.stderr
+    # the deck is echoed up to (not including) the offending line
+    assert "#InputFile:" in out and "units lj" in out and "foo bar" not in out
+
+
+@pytest.mark.parametrize("line,msg", [
+    ("variable x equal 1", "'variable' keyword is not supported"),
+    ("units si", "'units' command only supports"),
+    ("lattice bcc 1.0", "'lattice' command only supports 'sc' and 'fcc'"),
+    ("region box sphere 0 0 0 1", "'region' command only supports 'block'"),
+    ("pair_style eam", "'pair_style' command only supports"),
+    ("neigh_modify delay 5", "'neigh_modify' only supports 'every' and 'one'"),
+    ("comm_modify mode multi", "'comm_modify' command only supports single cutoff"),
+    ("fix 1 all nvt", "'fix' command only supports 'nve'"),
+    ("velocity all set 0 0 0", "'velocity' command can only be used with option 'create'"),
+    ("newton maybe", "'newton' must be followed by 'on' or 'off'"),
+    ("dump d all custom 10 f.txt", "'dump' command only supports 'vtk'"),
+    ("dump d all vtk 10 f.vtu", "requires '*' in file name"),
+])
+def test_deck_errors_follow_the_reference(tmp_path, line, msg):
+    p, out, err = run_cbnmd(tmp_path, line + "\n")
+    assert p.returncode != 0 and msg in err
+
+
+def test_unknown_cli_argument(tmp_path):
+    p, _, _ = run_cbnmd(tmp_path, "units lj\n", "--bogus")
+    assert p.returncode != 0 and "Unknown command line argument: --bogus" in p.stdout
+    p, _, _ = run_cbnmd(tmp_path, "units lj\n", "--kokkos-threads=4", "--device-type", "OPENMP")
+    assert p.returncode != 0 and "no CPU fallback" in p.stderr
+
+
+def test_no_gpu_fails_loudly(tmp_path):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p, out, err = run_cbnmd(tmp_path, DECK.format(c=4, steps=1))
+    assert p.returncode != 0
+    assert "no CUDA device available" in p.stderr and "no CPU fallback" in p.stderr
+    assert "Read input file." not in out  # stops at context creation
+
+
+# ------------------------------------------------------------------ GPU
+THERMO = re.compile(r"^(\d+)\t(-?\d+\.\d{6})\t(-?\d+\.\d{6})\t(-?\d+\.\d{6})\t(\d+\.\d{2})\t(\d\.\d{2}e[+-]\d{2})$")
+
+
+def parse_thermo(out):
+    rows = []
+    for ln in out.splitlines():
+        m = THERMO.match(ln)
+        if m:
+            rows.append((int(m.group(1)), float(m.group(2)), float(m.group(3)), float(m.group(4))))
+    return rows
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("layout", ["VERLET_2D", "VERLET_CSR"])
+def test_cbnmd_matches_oracle_thermo(tmp_path, half, layout):
+    import oracle_lib as O
+
+    cells, steps = 12, 60
+    args = ["--neigh-type", layout] + (["--force-iteration", "NEIGH_HALF"] if half else [])
+    p, out, err = run_cbnmd(tmp_path, DECK.format(c=cells, steps=steps), *args)
+    assert p.returncode == 0, p.stderr + err
+    rows = parse_thermo(out)
+    assert [r[0] for r in rows] == list(range(0, steps + 1, 10))
+
+    ref = O.Sim(mass=[2.0], half=half).create_lattice_fcc(cells=(cells,) * 3).setup()
+    ref.record_thermo()
+    ref.run(steps, 10)
+    want = np.array(ref.thermo())  # step, T, PE/N, KE/N
+    got = np.array(rows)
+    assert np.array_equal(got[:, 0], want[:, 0])
+    # six printed decimals
+    assert np.abs(got[:, 1] - want[:, 1]).max() <= 1.1e-6
+    assert np.abs(got[:, 2] - want[:, 2]).max() <= 1.1e-6
+    assert np.abs(got[:, 3] - (want[:, 2] + want[:, 3])).max() <= 2.1e-6
+
+    # layout of the output file
+    n = 4 * cells ** 3
+    assert out.startswith("\n#InputFile:\n#====")
+    assert "Read input file." in out
+    assert "Using: SystemVectorLength: 1 System:1AoSoA" in out
+    nb = "Neighbor:CabanaVerletHalf" if half else "Neighbor:CabanaVerletFull"
+    assert f"Using: Force:LJCabana {nb} Comm:CabanaMPI Binning:CabanaLinkedCell Integrator:NVE" in out
+    assert f"Atoms: {n} {n}" in out and "Created atoms." in out
+    assert "\n#Timestep Temperature PotE ETot Time Atomsteps/s \n" in out
+    assert re.search(rf"\n1 {n} \| \d+\.\d\d( \d+\.\d\d){{6}} \| PERFORMANCE\n", out)
+    assert re.search(rf"\n1 {n} \| 1\.00( \d+\.\d\d){{6}} \| FRACTION\n", out)
+    assert re.search(r"#Steps/s Atomsteps/s Atomsteps/\(proc\*s\)\n\d\.\d\de[+-]\d\d \d\.\d\de[+-]\d\d \d\.\d\de[+-]\d\d", out)
+
+
+@pytest.mark.gpu
+def test_cbnmd_inlj_step0_known_answer(tmp_path):
+    """in.lj geometry (40^3 cells, 256 000 atoms): T=1.400000 PotE=-6.332812 ETot=-4.232820
+    on the perfect lattice (SURVEY.md 8c iii)."""
+    p, out, err = run_cbnmd(tmp_path, DECK.format(c=40, steps=0))
+    assert p.returncode == 0, p.stderr + err
+    rows = parse_thermo(out)
+    assert rows[0] == (0, 1.4, -6.332812, -4.232820)
+    assert "Atoms: 256000 256000" in out
