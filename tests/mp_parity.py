@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check, launched with torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tests/mp_parity.py [--half]
+
+N NCCL ranks run the decomposed MD loop; rank 0 compares (a) the thermo trace and (b) the
+per-atom state by global id against the CPU oracle run with N virtual ranks AND with one
+rank (SURVEY.md test T7), and (c) per-rank ghost sets against the oracle's."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--half", action="store_true")
+    ap.add_argument("--steps", type=int, default=45)
+    ap.add_argument("--cells", type=int, default=8, help="fcc cells per dim per rank")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+
+    import cabanamd_b200 as cb
+    from bench import build_sim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    box = [cb.Context.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+
+    a = argparse.Namespace(cutoff=2.5, guess=50)
+    sim = build_sim(a, args.cells, args.half, world, rank, box[0], local)
+    sim.setup()
+    sim.record_thermo()
+    sim.run(args.steps, 5)
+    g = sim.ctx.get_atoms()
+    nl = g["n_local"]
+    mine = dict(id=g["id"][:nl], x=g["x"][:nl], v=g["v"][:nl], f=g["f"][:nl],
+                ghost_id=g["id"][nl:], ghost_x=g["x"][nl:], thermo=np.array(sim.thermo))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    ok = True
+    if rank == 0:
+        import oracle_lib as O
+        from cabanamd_b200.capi import dims_create
+
+        grid = dims_create(world)
+        cells = tuple(args.cells * k for k in grid)
+        worst = {}
+        for nr in (world, 1):
+            ref = O.Sim(mass=[2.0], half=args.half).create_lattice_fcc(cells=cells, nranks=nr).setup()
+            ref.record_thermo()
+            ref.run(args.steps, 5)
+            tg, to = np.array(gathered[0]["thermo"]), np.array(ref.thermo())
+            worst[f"thermo_vs_{nr}rank"] = float(np.abs(tg - to).max())
+            if nr != world:
+                continue  # ids are numbered per rank at creation: only thermo is comparable
+            ids = np.concatenate([d["id"] for d in gathered])
+            order = np.argsort(ids)
+            assert np.array_equal(ids[order], np.arange(1, len(ids) + 1)), "atoms lost or duplicated"
+            rid, rx, rv, rf = [], [], [], []
+            for rk in range(nr):
+                d = ref.get(rk)
+                n = d["n_local"]
+                rid.append(d["id"][:n]); rx.append(d["x"][:n]); rv.append(d["v"][:n]); rf.append(d["f"][:n])
+            ro = np.argsort(np.concatenate(rid))
+            for key, ours, theirs in (("x", "x", rx), ("v", "v", rv), ("f", "f", rf)):
+                A = np.concatenate([d[ours] for d in gathered])[order]
+                B = np.concatenate(theirs)[ro]
+                if key == "x":  # same atom may sit one box length apart before the next wrap
+                    L = np.array(cells) * ref.a
+                    diff = np.abs(A - B)
+                    diff = np.minimum(diff, np.abs(diff - L))
+                    worst[f"x_vs_{nr}rank"] = float(diff.max())
+                else:
+                    worst[f"{key}_vs_{nr}rank"] = float(np.abs(A - B).max() / np.abs(B).max())
+            if nr == world:
+                # ghost SETS per rank: (owner id, position) multiset equal to the oracle's
+                for rk in range(world):
+                    d = ref.get(rk)
+                    n = d["n_local"]
+                    want = np.concatenate([d["id"][n:, None].astype(np.float64), d["x"][n:]], axis=1)
+                    have = np.concatenate([gathered[rk]["ghost_id"][:, None].astype(np.float64),
+                                           gathered[rk]["ghost_x"]], axis=1)
+                    if want.shape != have.shape:
+                        worst[f"ghost_count_rank{rk}"] = float(abs(len(want) - len(have)))
+                        ok = False
+                        continue
+                    want = want[np.lexsort(want.T[::-1])]
+                    have = have[np.lexsort(have.T[::-1])]
+                    if not np.array_equal(want[:, 0], have[:, 0]):
+                        worst[f"ghost_ids_rank{rk}"] = 1.0
+                        ok = False
+                    worst[f"ghost_x_rank{rk}"] = float(np.abs(want[:, 1:] - have[:, 1:]).max())
+        tol = dict(thermo=1e-9, x=1e-9, v=1e-8, f=1e-8, ghost_x=1e-9)
+        for k, v in worst.items():
+            t = tol.get(k.split("_vs_")[0].split("_rank")[0], 0.0)
+            if not (v <= t):
+                ok = False
+        print(("MP_PARITY_OK " if ok else "MP_PARITY_FAIL ") + f"ranks={world} half={args.half} "
+              + " ".join(f"{k}={v:.2e}" for k, v in worst.items()), flush=True)
+    flag = [ok]
+    dist.broadcast_object_list(flag, src=0)
+    dist.barrier()
+    sim.ctx.close()
+    dist.destroy_process_group()
+    sys.exit(0 if flag[0] else 1)
+
+
+if __name__ == "__main__":
+    main()
