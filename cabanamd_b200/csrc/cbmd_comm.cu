@@ -577,20 +577,29 @@ __global__ void __launch_bounds__( 256 )
 
 extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
 {
-    CBMD_API_BEGIN
+    CBMD_API_BEGIN_NOJOIN
     TimedRegion timed__( ctx, CBMD_T_COMM );
     CBMD_REQUIRE( ctx->have_halo, "cbmd_exchange_halo must be called before cbmd_update_halo" );
+    cbmd_join_halo( ctx ); // a previous refresh nobody consumed
     ctx->epoch++;
-    cudaStream_t s = ctx->stream;
     if ( ctx->n_ghost == 0 )
         return 0;
     if ( ctx->flat_halo_ok )
     {
-        k_halo_update_flat<<<div_up( ctx->n_ghost, 256 ), 256, 0, s>>>(
+        k_halo_update_flat<<<div_up( ctx->n_ghost, 256 ), 256, 0, ctx->stream>>>(
             ctx->xt, ctx->n_local, ctx->n_ghost, ctx->ghost_owner, ctx->ghost_image, ctx->gext[0],
             ctx->gext[1], ctx->gext[2] );
         CBMD_LAUNCH_CHECK( ctx );
         return 0;
+    }
+    // multi-rank: the six dependent phases run on the comm stream so the force kernel can
+    // start on the interior tiles meanwhile (cbmd_force_lj joins before the boundary tiles)
+    const bool ov = ctx->overlap && ctx->tiles_valid;
+    cudaStream_t s = ov ? ctx->comm_stream : ctx->stream;
+    if ( ov )
+    {
+        CBMD_CUDA( cudaEventRecord( ctx->ev_x, ctx->stream ) );
+        CBMD_CUDA( cudaStreamWaitEvent( s, ctx->ev_x, 0 ) );
     }
     for ( int ph = 0; ph < 6; ph++ )
     {
@@ -628,6 +637,11 @@ extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
                                                                   d, P.shift );
             CBMD_LAUNCH_CHECK( ctx );
         }
+    }
+    if ( ov )
+    {
+        CBMD_CUDA( cudaEventRecord( ctx->ev_halo, s ) );
+        ctx->halo_pending = true;
     }
     CBMD_API_END
 }

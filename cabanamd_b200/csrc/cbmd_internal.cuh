@@ -124,6 +124,17 @@ struct cbmd_ctx
     bool flat_halo_ok = false;
     double *sendbuf = nullptr, *recvbuf = nullptr;
     size_t sendbuf_bytes = 0, recvbuf_bytes = 0;
+    // halo/compute overlap (multi-rank): update_halo runs on comm_stream while the force
+    // kernel works on the tiles that have no ghost neighbour; the boundary tiles wait on
+    // ev_halo.  tile_list = interior tiles (ascending) followed by boundary tiles.
+    cudaStream_t comm_stream = nullptr;
+    cudaStream_t aux_stream = nullptr; // boundary-tile force launch, concurrent with the interior tail
+    cudaEvent_t ev_x = nullptr, ev_halo = nullptr, ev_boundary = nullptr, ev_fready = nullptr;
+    bool halo_pending = false; // ghost positions are still in flight on comm_stream
+    int overlap = 1;           // option "overlap": 0 keeps everything on one stream
+    int *tile_list = nullptr, *tile_flag = nullptr;
+    int tile_cap = 0, n_tiles_interior = 0, n_tiles_boundary = 0;
+    bool tiles_valid = false;
 
     // scratch
     void *scratch = nullptr;
@@ -221,12 +232,18 @@ struct CbmdError : std::runtime_error
                              std::to_string( __LINE__ ) + ")" );                                  \
     } while ( 0 )
 
-#define CBMD_API_BEGIN                                                                            \
+// entry points that are aware of an in-flight halo update (force, update_halo)
+#define CBMD_API_BEGIN_NOJOIN                                                                     \
     try                                                                                           \
     {                                                                                             \
         if ( !ctx )                                                                               \
             throw CbmdError( "null context" );                                                    \
         CBMD_CUDA( cudaSetDevice( ctx->device ) );
+
+// every other entry point first orders the compute stream after a pending halo update
+#define CBMD_API_BEGIN                                                                            \
+    CBMD_API_BEGIN_NOJOIN                                                                         \
+    cbmd_join_halo( ctx );
 
 #define CBMD_API_END                                                                              \
     return 0;                                                                                     \
@@ -249,6 +266,14 @@ inline int64_t div_up64( int64_t a, int64_t b ) { return ( a + b - 1 ) / b; }
 
 // internal host helpers implemented across the .cu files
 void cbmd_ensure_capacity( cbmd_ctx *ctx, int n );
+inline void cbmd_join_halo( cbmd_ctx *ctx )
+{
+    if ( ctx->halo_pending )
+    {
+        cudaStreamWaitEvent( ctx->stream, ctx->ev_halo, 0 );
+        ctx->halo_pending = false;
+    }
+}
 void *cbmd_scratch( cbmd_ctx *ctx, size_t bytes );
 void cbmd_materialize_zero_force( cbmd_ctx *ctx );
 void cbmd_exclusive_scan_int( cbmd_ctx *ctx, int *data, int n ); // in place, data[n] = total

@@ -310,6 +310,91 @@ __global__ void __launch_bounds__( 256 )
         csr[o + n] = nb[nb_tile_base( i, nb_rows ) + (size_t)n * 32];
 }
 
+// ---------------------------------------------------------------------------
+// Interior / boundary tiles for the halo-compute overlap.  A ghost lies outside (or on)
+// the faces of the owned box, so an owned atom farther than r from every face has no
+// ghost in its row; a tile (32 consecutive atoms) whose atoms are all that far inside
+// can be processed while the ghost positions are still in flight.  The margin is
+// widened by 1e-9 relative so rounding can only make the test more conservative.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__( 256 )
+    k_tile_flags( const XT *__restrict__ xt, int n_local, double3 lo, double3 hi, double r,
+                  int *__restrict__ flag, int n_tiles )
+{
+    const int tile = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
+    const int lane = threadIdx.x & 31;
+    if ( tile >= n_tiles )
+        return;
+    const int i = tile * 32 + lane;
+    bool near = false;
+    if ( i < n_local )
+    {
+        const XT a = ld_xt( xt + i );
+        near = ( a.x - lo.x <= r ) || ( hi.x - a.x <= r ) || ( a.y - lo.y <= r ) || ( hi.y - a.y <= r ) ||
+               ( a.z - lo.z <= r ) || ( hi.z - a.z <= r );
+    }
+    const unsigned any = __ballot_sync( 0xffffffffu, near );
+    if ( lane == 0 )
+        flag[tile] = any ? 1 : 0;
+    if ( tile == 0 && lane == 0 )
+        flag[n_tiles] = 0;
+}
+
+// pos = exclusive scan of flag: interior tiles first (ascending), then boundary tiles
+__global__ void __launch_bounds__( 256 )
+    k_tile_partition( const int *__restrict__ flag, const int *__restrict__ pos, int n_tiles,
+                      int *__restrict__ list )
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( t >= n_tiles )
+        return;
+    const int nb = pos[n_tiles]; // number of boundary tiles
+    const int p = pos[t];
+    if ( flag[t] )
+        list[( n_tiles - nb ) + p] = t;
+    else
+        list[t - p] = t;
+}
+
+static void build_tile_lists( cbmd_ctx *ctx, double rcut )
+{
+    ctx->tiles_valid = false;
+    const int n_tiles = ( ctx->n_local + 31 ) >> 5;
+    if ( n_tiles == 0 || ctx->flat_halo_ok || !ctx->overlap || !ctx->have_halo )
+        return;
+    cudaStream_t s = ctx->stream;
+    if ( n_tiles + 1 > ctx->tile_cap )
+    {
+        if ( ctx->tile_list )
+        {
+            CBMD_CUDA( cudaStreamSynchronize( s ) );
+            CBMD_CUDA( cudaFree( ctx->tile_list ) );
+            CBMD_CUDA( cudaFree( ctx->tile_flag ) );
+        }
+        ctx->tile_cap = n_tiles + n_tiles / 4 + 64;
+        CBMD_CUDA( cudaMalloc( &ctx->tile_list, (size_t)ctx->tile_cap * sizeof( int ) ) );
+        CBMD_CUDA( cudaMalloc( &ctx->tile_flag, (size_t)ctx->tile_cap * sizeof( int ) ) );
+    }
+    int *pos = (int *)cbmd_scratch( ctx, (size_t)( n_tiles + 1 ) * sizeof( int ) );
+    const double r = rcut * ( 1.0 + 1e-9 );
+    k_tile_flags<<<div_up( n_tiles * 32, 256 ), 256, 0, s>>>(
+        ctx->xt, ctx->n_local, make_double3( ctx->llo[0], ctx->llo[1], ctx->llo[2] ),
+        make_double3( ctx->lhi[0], ctx->lhi[1], ctx->lhi[2] ), r, ctx->tile_flag, n_tiles );
+    CBMD_LAUNCH_CHECK( ctx );
+    CBMD_CUDA( cudaMemcpyAsync( pos, ctx->tile_flag, (size_t)( n_tiles + 1 ) * sizeof( int ),
+                                cudaMemcpyDeviceToDevice, s ) );
+    cbmd_exclusive_scan_int( ctx, pos, n_tiles );
+    k_tile_partition<<<div_up( n_tiles, 256 ), 256, 0, s>>>( ctx->tile_flag, pos, n_tiles,
+                                                             ctx->tile_list );
+    CBMD_LAUNCH_CHECK( ctx );
+    CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i + 2, pos + n_tiles, sizeof( int ),
+                                cudaMemcpyDeviceToHost, s ) );
+    CBMD_CUDA( cudaStreamSynchronize( s ) );
+    ctx->n_tiles_boundary = ctx->h_pinned_i[2];
+    ctx->n_tiles_interior = n_tiles - ctx->n_tiles_boundary;
+    ctx->tiles_valid = true;
+}
+
 extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layout,
                                  int max_neigh_guess, int *max_neigh_guess_out )
 {
@@ -396,6 +481,7 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
         CBMD_REQUIRE( attempt < 2, "neighbour list did not converge" );
     }
     ctx->nb_max = observed;
+    build_tile_lists( ctx, rcut );
     // neighbor_verlet.h:60-61: max_neigh_guess = current_max * 1.1 when exceeded
     int guess = max_neigh_guess;
     if ( observed > guess )

@@ -212,7 +212,19 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
                              std::to_string( prop.minor ) + ")" );
         cbmd_ctx *ctx = new cbmd_ctx;
         ctx->device = device;
+        if ( const char *e = getenv( "CBMD_OVERLAP" ) ) // A/B switch for measurements
+            ctx->overlap = atoi( e );
         CBMD_CUDA( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
+        {
+            int lo = 0, hi = 0; // comm stream gets the highest priority so its small kernels
+            CBMD_CUDA( cudaDeviceGetStreamPriorityRange( &lo, &hi ) ); // slip in between force CTAs
+            CBMD_CUDA( cudaStreamCreateWithPriority( &ctx->comm_stream, cudaStreamNonBlocking, hi ) );
+            CBMD_CUDA( cudaEventCreateWithFlags( &ctx->ev_x, cudaEventDisableTiming ) );
+            CBMD_CUDA( cudaEventCreateWithFlags( &ctx->ev_halo, cudaEventDisableTiming ) );
+            CBMD_CUDA( cudaStreamCreateWithFlags( &ctx->aux_stream, cudaStreamNonBlocking ) );
+            CBMD_CUDA( cudaEventCreateWithFlags( &ctx->ev_boundary, cudaEventDisableTiming ) );
+            CBMD_CUDA( cudaEventCreateWithFlags( &ctx->ev_fready, cudaEventDisableTiming ) );
+        }
         memset( &ctx->mass, 0, sizeof( ctx->mass ) );
         memset( &ctx->lj, 0, sizeof( ctx->lj ) );
         ctx->lj.ntypes = 1;
@@ -241,13 +253,24 @@ extern "C" int cbmd_destroy( cbmd_ctx *ctx )
         return 0;
     cudaSetDevice( ctx->device );
     cudaStreamSynchronize( ctx->stream );
+    if ( ctx->comm_stream )
+    {
+        cudaStreamSynchronize( ctx->comm_stream );
+        cudaStreamDestroy( ctx->comm_stream );
+        cudaEventDestroy( ctx->ev_x );
+        cudaEventDestroy( ctx->ev_halo );
+        cudaStreamSynchronize( ctx->aux_stream );
+        cudaStreamDestroy( ctx->aux_stream );
+        cudaEventDestroy( ctx->ev_boundary );
+        cudaEventDestroy( ctx->ev_fready );
+    }
     void *ptrs[] = { ctx->xt,         ctx->xt_alt,      ctx->v,          ctx->v_alt,
                      ctx->f,          ctx->f_alt,       ctx->id,         ctx->id_alt,
                      ctx->q,          ctx->q_alt,       ctx->cell_start, ctx->cell_cursor,
                      ctx->cell_atoms, ctx->atom_cell,   ctx->perm,       ctx->nb,
                      ctx->nb_count,   ctx->ghost_owner, ctx->ghost_image, ctx->sendbuf,
                      ctx->recvbuf,    ctx->scratch,     ctx->d_red,      ctx->d_flags,
-                     ctx->pe_partial };
+                     ctx->pe_partial, ctx->tile_list, ctx->tile_flag };
     for ( void *p : ptrs )
         if ( p )
             cudaFree( p );
@@ -286,6 +309,8 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
     std::string n( name ? name : "" );
     if ( n == "force_variant" )
         ctx->force_variant = (int)value;
+    else if ( n == "overlap" )
+        ctx->overlap = (int)value;
     else
         throw CbmdError( "unknown option: " + n );
     CBMD_API_END
