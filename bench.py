@@ -163,8 +163,8 @@ def timed_steps(sim, k, thermo, dist_ctx):
     torch.cuda.synchronize()
     e0.record(stream)
     sim.run(k * MD_PER_STEP, thermo)
+    sim.ctx.sync()  # also applies the deferred final_integrate of the last step
     e1.record(stream)
-    sim.ctx.sync()
     torch.cuda.synchronize()
     barrier(dist_ctx)
     sec = e0.elapsed_time(e1) * 1e-3
@@ -269,8 +269,8 @@ def measure_e2e(args, sim, steps, dist_ctx):
     e0.record(stream)
     for _ in range(steps):
         one_step()
-    e1.record(stream)
     ctx.sync()
+    e1.record(stream)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     barrier(dist_ctx)

@@ -71,19 +71,43 @@ __global__ void __launch_bounds__( 256 )
     }
 }
 
-// returns the number of selected indices; pos (device, n+1 ints) holds the exclusive scan
-static int select_face( cbmd_ctx *ctx, int n, int d, int mode, double thr, int **pos_out )
+// Selects the atoms of [0,n) passing the face test and, when the phase has a remote peer,
+// swaps the send count with it — the count travels device to device (no host staging) and
+// both numbers come back in ONE read-back, so a phase costs a single host synchronisation.
+// pos (device, n+1 ints) holds the exclusive scan of the flags.
+static void select_face( cbmd_ctx *ctx, int n, int d, int mode, double thr, bool remote,
+                         int peer_send, int peer_recv, int **pos_out, int *n_send, int *n_recv )
 {
-    int *pos = (int *)cbmd_scratch( ctx, (size_t)( n + 1 ) * sizeof( int ) );
     cudaStream_t s = ctx->stream;
-    k_face_flags<<<div_up( n + 1, 256 ), 256, 0, s>>>( ctx->xt, n, d, mode, thr, pos );
-    CBMD_LAUNCH_CHECK( ctx );
-    cbmd_exclusive_scan_int( ctx, pos, n );
-    CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i, pos + n, sizeof( int ), cudaMemcpyDeviceToHost,
-                                s ) );
+    int *pos = nullptr;
+    const int *d_count = nullptr;
+    if ( n > 0 )
+    {
+        pos = (int *)cbmd_scratch( ctx, (size_t)( n + 1 ) * sizeof( int ) );
+        k_face_flags<<<div_up( n + 1, 256 ), 256, 0, s>>>( ctx->xt, n, d, mode, thr, pos );
+        CBMD_LAUNCH_CHECK( ctx );
+        cbmd_exclusive_scan_int( ctx, pos, n );
+        d_count = pos + n;
+    }
+    else
+    {
+        CBMD_CUDA( cudaMemsetAsync( ctx->d_flags + 18, 0, sizeof( int ), s ) );
+        d_count = ctx->d_flags + 18;
+    }
+    CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i, d_count, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
+    if ( remote )
+    {
+        int *d_in = ctx->d_flags + 17;
+        CBMD_NCCL( ncclGroupStart() );
+        CBMD_NCCL( ncclSend( d_count, 1, ncclInt, peer_send, ctx->nccl, s ) );
+        CBMD_NCCL( ncclRecv( d_in, 1, ncclInt, peer_recv, ctx->nccl, s ) );
+        CBMD_NCCL( ncclGroupEnd() );
+        CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i + 1, d_in, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
+    }
     CBMD_CUDA( cudaStreamSynchronize( s ) );
     *pos_out = pos;
-    return ctx->h_pinned_i[0];
+    *n_send = ctx->h_pinned_i[0];
+    *n_recv = remote ? ctx->h_pinned_i[1] : ctx->h_pinned_i[0];
 }
 
 // ---------------------------------------------------------------------------
@@ -242,23 +266,6 @@ static void ensure_buf( double *&buf, size_t &have, size_t bytes, cudaStream_t s
     CBMD_CUDA( cudaMalloc( &buf, have ) );
 }
 
-// exchange one int with the phase peers (send to peer_send, receive from peer_recv)
-static int swap_count( cbmd_ctx *ctx, int mine, int peer_send, int peer_recv )
-{
-    int *d = ctx->d_flags + 16;
-    cudaStream_t s = ctx->stream;
-    ctx->h_pinned_i[8] = mine;
-    CBMD_CUDA( cudaMemcpyAsync( d, ctx->h_pinned_i + 8, sizeof( int ), cudaMemcpyHostToDevice, s ) );
-    CBMD_NCCL( ncclGroupStart() );
-    CBMD_NCCL( ncclSend( d, 1, ncclInt, peer_send, ctx->nccl, s ) );
-    CBMD_NCCL( ncclRecv( d + 1, 1, ncclInt, peer_recv, ctx->nccl, s ) );
-    CBMD_NCCL( ncclGroupEnd() );
-    CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i + 9, d + 1, sizeof( int ), cudaMemcpyDeviceToHost,
-                                s ) );
-    CBMD_CUDA( cudaStreamSynchronize( s ) );
-    return ctx->h_pinned_i[9];
-}
-
 static void phase_peers( const cbmd_ctx *ctx, int ph, int &peer_send, int &peer_recv )
 {
     // comm_mpi_impl.h:87-99: send +x,-x,+y,-y,+z,-z; recv = send of the opposite phase
@@ -309,10 +316,8 @@ extern "C" int cbmd_exchange( cbmd_ctx *ctx, int *n_sent_global )
             shift = ctx->gext[d];
         n = ctx->n_local;
         int *pos = nullptr;
-        int n_send = 0;
-        if ( n > 0 )
-            n_send = select_face( ctx, n, d, mode, thr, &pos );
-        const int n_recv = swap_count( ctx, n_send, peer_send, peer_recv );
+        int n_send = 0, n_recv = 0;
+        select_face( ctx, n, d, mode, thr, true, peer_send, peer_recv, &pos, &n_send, &n_recv );
         ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, (size_t)( n_send + 1 ) * sizeof( MigTuple ), s );
         ensure_buf( ctx->recvbuf, ctx->recvbuf_bytes, (size_t)( n_recv + 1 ) * sizeof( MigTuple ), s );
         if ( n_send > 0 )
@@ -447,7 +452,7 @@ extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
         const int mode = ( ph % 2 == 0 ) ? 0 : 1;
         const double thr = ( ph % 2 == 0 ) ? ctx->lhi[d] - comm_depth : ctx->llo[d] + comm_depth;
         int *pos = nullptr;
-        P.n_send = np > 0 ? select_face( ctx, np, d, mode, thr, &pos ) : 0;
+        select_face( ctx, np, d, mode, thr, !self, P.peer_send, P.peer_recv, &pos, &P.n_send, &P.n_recv );
         if ( P.n_send > P.send_cap )
         {
             if ( P.send_idx )
@@ -483,8 +488,6 @@ extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
         }
         else
         {
-            P.n_recv = swap_count( ctx, P.n_send, P.peer_send, P.peer_recv );
-            ctx->n_ghost += 0;
             cbmd_ensure_capacity( ctx, first + P.n_recv );
             const size_t sb = (size_t)( P.n_send + 1 ) * ( sizeof( XT ) + sizeof( int ) ) + 64;
             ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, sb, s );

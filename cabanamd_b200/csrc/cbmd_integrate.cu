@@ -48,28 +48,39 @@ __global__ void __launch_bounds__( 256 )
         __dadd_rn( v[2 * (size_t)cap + i], __dmul_rn( dtfm, f[2 * (size_t)cap + i] ) );
 }
 
-extern "C" int cbmd_integrate_initial( cbmd_ctx *ctx )
+// final_integrate of step k followed by initial_integrate of step k+1 (same f):
+// v1 = v + dtfm*f; v2 = v1 + dtfm*f; x += dt*v2 — the identical sequence of roundings
+__global__ void __launch_bounds__( 256 )
+    k_integrate_final_initial( XT *__restrict__ xt, double *__restrict__ v,
+                               const double *__restrict__ f, int cap, int n,
+                               const __grid_constant__ MassTable mt, double dtv )
 {
-    CBMD_API_BEGIN
-    TimedRegion timed__( ctx, CBMD_T_INTEGRATE );
-    cbmd_materialize_zero_force( ctx );
-    ctx->epoch++;
-    const int n = ctx->n_local;
-    if ( n > 0 )
-    {
-        k_integrate_initial<<<div_up( n, 256 ), 256, 0, ctx->stream>>>( ctx->xt, ctx->v, ctx->f,
-                                                                     ctx->cap, n, ctx->mass,
-                                                                     ctx->dt );
-        CBMD_LAUNCH_CHECK( ctx );
-    }
-    CBMD_API_END
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    XT r = xt[i];
+    const double dtfm = mt.dtfm[r.t];
+    double vx = v[i], vy = v[(size_t)cap + i], vz = v[2 * (size_t)cap + i];
+    const double kx = __dmul_rn( dtfm, f[i] ), ky = __dmul_rn( dtfm, f[(size_t)cap + i] ),
+                 kz = __dmul_rn( dtfm, f[2 * (size_t)cap + i] );
+    vx = __dadd_rn( __dadd_rn( vx, kx ), kx );
+    vy = __dadd_rn( __dadd_rn( vy, ky ), ky );
+    vz = __dadd_rn( __dadd_rn( vz, kz ), kz );
+    r.x = __dadd_rn( r.x, __dmul_rn( dtv, vx ) );
+    r.y = __dadd_rn( r.y, __dmul_rn( dtv, vy ) );
+    r.z = __dadd_rn( r.z, __dmul_rn( dtv, vz ) );
+    v[i] = vx;
+    v[(size_t)cap + i] = vy;
+    v[2 * (size_t)cap + i] = vz;
+    xt[i] = r;
 }
 
-extern "C" int cbmd_integrate_final( cbmd_ctx *ctx )
+void cbmd_materialize_final( cbmd_ctx *ctx )
 {
-    CBMD_API_BEGIN
+    if ( !ctx->final_pending )
+        return;
+    ctx->final_pending = false;
     TimedRegion timed__( ctx, CBMD_T_INTEGRATE );
-    cbmd_materialize_zero_force( ctx );
     const int n = ctx->n_local;
     if ( n > 0 )
     {
@@ -77,6 +88,36 @@ extern "C" int cbmd_integrate_final( cbmd_ctx *ctx )
                                                                    ctx->cap, n, ctx->mass );
         CBMD_LAUNCH_CHECK( ctx );
     }
+}
+
+extern "C" int cbmd_integrate_initial( cbmd_ctx *ctx )
+{
+    CBMD_API_BEGIN_NOJOIN
+    cbmd_join_halo( ctx );
+    TimedRegion timed__( ctx, CBMD_T_INTEGRATE );
+    cbmd_materialize_zero_force( ctx );
+    ctx->epoch++;
+    const int n = ctx->n_local;
+    const bool fused = ctx->final_pending;
+    ctx->final_pending = false;
+    if ( n > 0 )
+    {
+        if ( fused )
+            k_integrate_final_initial<<<div_up( n, 256 ), 256, 0, ctx->stream>>>(
+                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt );
+        else
+            k_integrate_initial<<<div_up( n, 256 ), 256, 0, ctx->stream>>>(
+                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt );
+        CBMD_LAUNCH_CHECK( ctx );
+    }
+    CBMD_API_END
+}
+
+extern "C" int cbmd_integrate_final( cbmd_ctx *ctx )
+{
+    CBMD_API_BEGIN // a still-pending earlier final (two finals in a row) is applied here
+    cbmd_materialize_zero_force( ctx );
+    ctx->final_pending = true; // applied by the next entry point (fused if it is initial_integrate)
     CBMD_API_END
 }
 

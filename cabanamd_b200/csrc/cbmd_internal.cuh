@@ -79,6 +79,10 @@ struct cbmd_ctx
     int *id = nullptr, *id_alt = nullptr;
     double *q = nullptr, *q_alt = nullptr;
     bool f_zero_pending = false; // deferred deep_copy(f,0): fused into the full-list force kernel
+    // deferred Integrator::final_integrate: when the next call is initial_integrate the two
+    // half kicks and the drift run as ONE streaming kernel (same roundings, 43 % less traffic);
+    // any other entry point materialises it first
+    bool final_pending = false;
     // positions/list epoch: bumped by every call that moves atoms or rebuilds the list;
     // validates the pair energy cached by a fused force+energy sweep
     uint64_t epoch = 1;
@@ -241,9 +245,11 @@ struct CbmdError : std::runtime_error
         CBMD_CUDA( cudaSetDevice( ctx->device ) );
 
 // every other entry point first orders the compute stream after a pending halo update
+// and applies a deferred final_integrate
 #define CBMD_API_BEGIN                                                                            \
     CBMD_API_BEGIN_NOJOIN                                                                         \
-    cbmd_join_halo( ctx );
+    cbmd_join_halo( ctx );                                                                        \
+    cbmd_materialize_final( ctx );
 
 #define CBMD_API_END                                                                              \
     return 0;                                                                                     \
@@ -276,6 +282,7 @@ inline void cbmd_join_halo( cbmd_ctx *ctx )
 }
 void *cbmd_scratch( cbmd_ctx *ctx, size_t bytes );
 void cbmd_materialize_zero_force( cbmd_ctx *ctx );
+void cbmd_materialize_final( cbmd_ctx *ctx );
 void cbmd_exclusive_scan_int( cbmd_ctx *ctx, int *data, int n ); // in place, data[n] = total
 
 // ---------------------------------------------------------------------------

@@ -449,3 +449,33 @@ def test_neighbor_build_hard_cases(cb):
     assert np.array_equal(counts, ref.arrays()[0])
     for a, b in zip(rows, ref.rows_sorted()):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_1000_step_thermo_and_energy_drift_match_oracle(cb, half):
+    """T8 (north star: "thermo energies must agree over 1000 steps with matching energy
+    drift"): 4 000 atoms, 1000 NVE steps, thermo every 10.  The trajectories are chaotic,
+    so round-off differences grow; the thermo trace still agrees to 1e-6 and the total
+    energy drift (last - first ETot, and its rms fluctuation) agrees to 1e-7."""
+    from cabanamd_b200.harness import Simulation
+
+    s0 = O.Sim(mass=[2.0], half=half).create_lattice_fcc(cells=(10, 10, 10))
+    d, dom = s0.get(), s0.domain()
+    s0.setup()
+    sim = Simulation(half=half)
+    sim.set_box(dom["llo"], dom["lhi"])
+    sim.set_atoms(d["x"], d["v"], d["type"], d["id"])
+    sim.setup()
+    s0.record_thermo()
+    sim.record_thermo()
+    s0.run(1000, 10)
+    sim.run(1000, 10)
+    tg, to = np.array(sim.thermo), np.array(s0.thermo())
+    assert tg.shape == to.shape == (101, 4)
+    assert np.abs(tg[:, 1:] - to[:, 1:]).max() < 1e-6
+    eg, eo = tg[:, 2] + tg[:, 3], to[:, 2] + to[:, 3]
+    drift_g, drift_o = eg[-1] - eg[0], eo[-1] - eo[0]
+    assert abs(drift_g - drift_o) < 1e-7
+    assert abs(eg.std() - eo.std()) < 1e-7
+    if not half:  # full-list PE is the physical one: NVE conserves ETot to ~1e-4 per atom
+        assert abs(drift_g) < 5e-4
