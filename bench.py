@@ -443,6 +443,20 @@ def main():
                 "stored_neighbours_per_atom": m2["nn"],
                 "note": "1 M-atom position array (32 MB) fits the 126 MB L2"}
             s2.ctx.close()
+        # configs[4]: long cutoff, rc = 5.0 sigma (~526 stored neighbours per atom), 1 M atoms
+        a5 = argparse.Namespace(**vars(args))
+        a5.half, a5.cutoff, a5.guess, a5.melt = False, 5.0, 600, 40
+        s5 = build_sim(a5, 63, False, 1, 0, None, local)
+        s5.setup()
+        m5 = measure_resident(a5, s5, 2, 1, None, False)
+        f_ms, f_n = m5["timing"]["force_kernel"]
+        fb5 = force_bytes(m5["n_local"], m5["n_ghost"], m5["nn"], False)
+        extra["configs[4] 1M atoms rc=5.0 full list"] = {
+            "value": s5.N * 2 * MD_PER_STEP / m5["sec"], "unit": UNIT, "atoms": s5.N,
+            "force_kernel_ms": f_ms / max(f_n, 1),
+            "force_kernel_GBps_algorithmic": fb5 / (f_ms / max(f_n, 1) * 1e-3) / 1e9,
+            "stored_neighbours_per_atom": m5["nn"], "ghost_fraction": m5["n_ghost"] / m5["n_local"]}
+        s5.ctx.close()
 
     cpu = None
     if rank == 0 and n == 1 and not args.no_cpu:

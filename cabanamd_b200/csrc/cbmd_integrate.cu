@@ -164,17 +164,40 @@ __global__ void __launch_bounds__( 256 )
     k_final_sum( const double *__restrict__ partial, int nparts, int nvals,
                  double *__restrict__ out )
 {
-    // out[k] = sum_b partial[k*nparts + b]
+    // out[k*gridDim.x + blockIdx.x] = sum of this block's contiguous chunk of
+    // partial[k*nparts + ...]; with one block: out[k] = sum_b partial[k*nparts + b].
+    // Fixed chunking and a fixed tree: deterministic.
     __shared__ double sh[8];
+    const int chunk = ( nparts + gridDim.x - 1 ) / gridDim.x;
+    const int b0 = blockIdx.x * chunk, b1 = min( nparts, b0 + chunk );
     for ( int k = 0; k < nvals; k++ )
     {
         double acc = 0.0;
-        for ( int b = threadIdx.x; b < nparts; b += blockDim.x )
+#pragma unroll 4
+        for ( int b = b0 + threadIdx.x; b < b1; b += blockDim.x )
             acc += partial[(size_t)k * nparts + b];
         const double s = block_sum_256( acc, sh );
         if ( threadIdx.x == 0 )
-            out[k] = s;
+            out[(size_t)k * gridDim.x + blockIdx.x] = s;
     }
+}
+
+// two-level deterministic sum of nvals rows of nparts partials into out[0..nvals)
+void cbmd_reduce_partials( cbmd_ctx *ctx, const double *partial, int nparts, int nvals, double *out )
+{
+    cudaStream_t s = ctx->stream;
+    if ( nparts <= 4096 )
+    {
+        k_final_sum<<<1, 256, 0, s>>>( partial, nparts, nvals, out );
+        CBMD_LAUNCH_CHECK( ctx );
+        return;
+    }
+    const int g = 128;
+    double *mid = ctx->d_red + 48000; // 128 x nvals (<= 8) doubles of the 64 K scratch
+    k_final_sum<<<g, 256, 0, s>>>( partial, nparts, nvals, mid );
+    CBMD_LAUNCH_CHECK( ctx );
+    k_final_sum<<<1, 256, 0, s>>>( mid, g, nvals, out );
+    CBMD_LAUNCH_CHECK( ctx );
 }
 
 extern "C" int cbmd_sum_mv2( cbmd_ctx *ctx, double *sum )
@@ -193,8 +216,7 @@ extern "C" int cbmd_sum_mv2( cbmd_ctx *ctx, double *sum )
         nblk = 1184; // 148 SMs x 8 resident CTAs
     k_sum_mv2<<<nblk, 256, 0, ctx->stream>>>( ctx->xt, ctx->v, ctx->cap, n, ctx->mass, ctx->d_red );
     CBMD_LAUNCH_CHECK( ctx );
-    k_final_sum<<<1, 256, 0, ctx->stream>>>( ctx->d_red, nblk, 1, ctx->d_red + 32768 );
-    CBMD_LAUNCH_CHECK( ctx );
+    cbmd_reduce_partials( ctx, ctx->d_red, nblk, 1, ctx->d_red + 32768 );
     CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned, ctx->d_red + 32768, sizeof( double ),
                                 cudaMemcpyDeviceToHost, ctx->stream ) );
     CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );

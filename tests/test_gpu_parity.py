@@ -479,3 +479,31 @@ def test_1000_step_thermo_and_energy_drift_match_oracle(cb, half):
     assert abs(eg.std() - eo.std()) < 1e-7
     if not half:  # full-list PE is the physical one: NVE conserves ETot to ~1e-4 per atom
         assert abs(drift_g) < 5e-4
+
+
+def test_long_cutoff_variant_matches_oracle(cb):
+    """BASELINE configs[4]: rc = 5.0 sigma, skin 0.3 (~526 stored neighbours per atom, row
+    capacity regrown from the 'one 600' guess): sets bit-exact, forces 1e-10, thermo."""
+    from cabanamd_b200.harness import Simulation
+
+    s0 = O.Sim(mass=[2.0], cut=5.0).create_lattice_fcc(cells=(8, 8, 8))
+    d, dom = s0.get(), s0.domain()
+    s0.setup()
+    sim = Simulation(cut=5.0, max_neigh_guess=600)
+    sim.set_box(dom["llo"], dom["lhi"])
+    sim.set_atoms(d["x"], d["v"], d["type"], d["id"])
+    sim.setup()
+    c, o, n = sim.ctx.neigh_get()
+    oc, oo, on = s0.list()
+    assert np.array_equal(c, oc) and c[: len(oo) - 1].mean() > 500
+    for i in range(0, len(oo) - 1, 5):
+        assert np.array_equal(np.sort(n[o[i]:o[i + 1]]), np.sort(on[oo[i]:oo[i + 1]]))
+    s0.record_thermo()
+    sim.record_thermo()
+    s0.run(40, 10)
+    sim.run(40, 10)
+    assert np.abs(np.array(sim.thermo) - np.array(s0.thermo())).max() < 1e-9
+    a, b = sim.ctx.get_atoms(), s0.get()
+    fa = a["f"][: a["n_local"]][np.argsort(a["id"][: a["n_local"]])]
+    fb = b["f"][: b["n_local"]][np.argsort(b["id"][: b["n_local"]])]
+    assert np.abs(fa - fb).max() <= 1e-9 * np.abs(fb).max()
