@@ -7,8 +7,10 @@
 #include <chrono>
 #include <fstream>
 #include <iomanip>
+#include <memory>
 #include <string>
 
+#include "binary_dump.h"
 #include "binning.h"
 #include "comm.h"
 #include "force.h"
@@ -18,7 +20,9 @@
 #include "neighbor.h"
 #include "output.h"
 #include "property.h"
+#include "read_data.h"
 #include "system.h"
+#include "vtk_writer.h"
 
 class CabanaMD
 {
@@ -44,6 +48,7 @@ class CbnMD : public CabanaMD
     Comm<t_System> *comm = nullptr;
     InputFile<t_System> *input = nullptr;
     Binning<t_System> *binning = nullptr;
+    std::unique_ptr<VTKWriter::AsyncWriter> vtk; // created on the first particle dump
 
     ~CbnMD() override
     {
@@ -73,8 +78,6 @@ class CbnMD : public CabanaMD
 
         if ( input->force_type == FORCE_NNP )
             log_err( err, "NNP requested, but not compiled!" );
-        if ( input->read_data_flag )
-            log_err( err, "read_data is not supported in this build" );
 
         const auto neigh_cutoff = input->force_cutoff + input->neighbor_skin;
         const bool half_neigh = input->force_iteration_type == FORCE_ITER_NEIGH_HALF;
@@ -96,7 +99,21 @@ class CbnMD : public CabanaMD
         log( out, "Using: ", force->name(), " ", neighbor->name(), " ", comm->name(), " ", binning->name(),
              " ", integrator->name() );
 
-        if ( system->N == 0 )
+        // atoms: LAMMPS data file or fcc/sc lattice (cabanamd_impl.h:185-194)
+        if ( system->N == 0 && input->read_data_flag )
+        {
+            const int ntypes_before = system->ntypes;
+            read_lammps_data_file( input, system, comm );
+            if ( system->ntypes != ntypes_before )
+            {
+                // the type count came from the file header: size the pair tables for it
+                // (the reference sizes them once, before any atoms exist)
+                delete force;
+                force = new ForceLJ<t_System, t_Neighbor>( system );
+                force->init_coeff( input->force_coeff_lines );
+            }
+        }
+        else if ( system->N == 0 )
             input->create_lattice( comm );
         log( out, "Created atoms." );
 
@@ -123,6 +140,11 @@ class CbnMD : public CabanaMD
             const auto KE = kine.compute( system ) / system->N;
             print_summary( out, 0, T, PE, KE, 0.0, 0.0 );
         }
+
+        if ( input->dumpbinaryflag )
+            dump_binary( 0 );
+        if ( input->correctnessflag )
+            check_correctness( 0 );
     }
 
     void run() override
@@ -182,9 +204,21 @@ class CbnMD : public CabanaMD
                 print_summary( out, step, T, PE, KE, time, rate );
                 last_time = time;
             }
-            // `dump ... vtk` is parsed but particle dumps are out of scope;
-            // vtk_rate == 0 means never (the reference divides by zero here)
+            // vtk_rate == 0 (no `dump` line) means never; the reference takes step % 0 here
+            if ( input->vtk_rate > 0 && step % input->vtk_rate == 0 )
+            {
+                if ( !vtk )
+                    vtk = std::make_unique<VTKWriter::AsyncWriter>();
+                VTKWriter::writeParticles( *vtk, comm->process_rank(), comm->num_processes(), step, system,
+                                           input->vtk_file, err );
+            }
+            if ( input->dumpbinaryflag )
+                dump_binary( step );
+            if ( input->correctnessflag )
+                check_correctness( step );
         }
+        if ( vtk && vtk->drain() > 0 )
+            log( err, "Warning: ", vtk->drain(), " VTK particle file(s) could not be written" );
 
         cbmd_check( cbmd_sync( system->ctx ), "cbmd_sync" );
         const double time = seconds();
@@ -222,11 +256,66 @@ class CbnMD : public CabanaMD
                  " steps with ", system->N, " atoms" );
 
         if ( input->write_data_flag )
-            log( err, "Warning: write_data is not supported in this build; no data file written" );
+        {
+            system->deep_copy_to_host();
+            write_data( system, comm, input->output_data_file, input->write_data_precision );
+        }
     }
 
-    void dump_binary( int ) override {}
-    void check_correctness( int ) override {}
+    // cabanamd_impl.h:434-474
+    void dump_binary( int step ) override
+    {
+        if ( input->dumpbinary_rate <= 0 || step % input->dumpbinary_rate )
+            return;
+        std::ofstream err( input->error_file, std::ofstream::app );
+        system->deep_copy_to_host();
+        const std::string file = BinaryDump::file_name( input->dumpbinary_path, step, comm->process_rank() );
+        if ( !BinaryDump::write( file, system->N_local, system->id.data(), system->type.data(),
+                                 system->q.data(), system->x.data(), system->v.data(), system->f.data() ) )
+        {
+            log_err( err, "Cannot open dump file: ", file );
+            throw std::runtime_error( "Cannot open dump file: " + file );
+        }
+    }
+
+    // cabanamd_impl.h:484-642
+    void check_correctness( int step ) override
+    {
+        if ( input->correctness_rate <= 0 || step % input->correctness_rate )
+            return;
+        std::ofstream err( input->error_file, std::ofstream::app );
+        system->deep_copy_to_host();
+        const std::string file = BinaryDump::file_name( input->reference_path, step, comm->process_rank() );
+        BinaryDump::State ref;
+        const char *problem = nullptr;
+        switch ( BinaryDump::read( file, system->N_local, ref ) )
+        {
+        case BinaryDump::READ_CANNOT_OPEN:
+            problem = "Cannot open input file: ";
+            break;
+        case BinaryDump::READ_COUNT_MISMATCH:
+            problem = "Mismatch in current and reference atom counts: ";
+            break;
+        case BinaryDump::READ_SHORT:
+            problem = "Error reading reference data: ";
+            break;
+        default:
+            break;
+        }
+        if ( problem )
+        {
+            log_err( err, problem, file );
+            throw std::runtime_error( problem + file );
+        }
+        BinaryDump::Deltas d = BinaryDump::compare( system->N_local, system->id.data(), system->x.data(),
+                                                    system->v.data(), system->f.data(), ref );
+        if ( d.unmatched_id >= 0 )
+            log( err, "Unable to find current id matching reference id: ", d.unmatched_id );
+        comm->reduce_float( d.sumsq, 3 );
+        comm->reduce_max_float( d.maxabs, 3 );
+        if ( comm->process_rank() == 0 && !BinaryDump::append_report( input->correctness_file, step, d.sumsq, d.maxabs ) )
+            log( err, "Warning: cannot write correctness file ", input->correctness_file );
+    }
 
     void print_summary( std::ofstream &out, int step, T_V_FLOAT T, T_F_FLOAT PE, T_V_FLOAT KE, double time,
                         double rate, T_INT = -1 )

@@ -18,8 +18,9 @@ const char *usage =
     "  --force-iteration [TYPE]     NEIGH_FULL | NEIGH_HALF\n"
     "  --neigh-parallel [TYPE]      SERIAL | TEAM | TEAM_VECTOR (accepted; one kernel serves all)\n"
     "  --neigh-type [TYPE]          VERLET_2D | VERLET_CSR\n"
-    "  --dumpbinary [N] [PATH]      accepted, unused (dead in the reference too)\n"
-    "  --correctness [N] [PATH] [FILE]  accepted, unused\n"
+    "  --dumpbinary [N] [PATH]      every N steps write PATH/output.<step>.<rank> (binary state)\n"
+    "  --correctness [N] [PATH] [FILE]  every N steps compare with PATH/output.* (id-matched\n"
+    "                               l2 / max deltas of x, v, f), one line per step in FILE\n"
     "  --vacuum [N]                 enlarge the box N (>1) times\n";
 
 bool is( const char *a, const char *b ) { return std::strcmp( a, b ) == 0; }

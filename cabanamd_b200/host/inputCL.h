@@ -19,7 +19,7 @@ class InputCL
     bool vacuum = false;
     double vacuum_rate = 1.0;
 
-    // accepted for compatibility; dead in the reference as well
+    // binary state dumps / regression check (binary_dump.h); InputFile copies them
     int dumpbinary_rate = 0, correctness_rate = 0;
     bool dumpbinaryflag = false, correctnessflag = false;
     const char *dumpbinary_path = nullptr, *reference_path = nullptr, *correctness_file = nullptr;

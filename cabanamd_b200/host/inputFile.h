@@ -145,9 +145,13 @@ class InputFile
     T_INT max_neigh_guess = 50;
 
     int thermo_rate = 10;
-    // never set from the command line in the reference either
+    // `--dumpbinary` / `--correctness` (binary_dump.h).  The reference parses them in
+    // InputCL but never copies them here; this build does.
+    int dumpbinary_rate = 0, correctness_rate = 0;
     bool dumpbinaryflag = false, correctnessflag = false;
+    std::string dumpbinary_path, reference_path, correctness_file;
     std::string input_data_file, output_data_file;
+    int write_data_precision = 6; // stream default, as the reference writes
     bool read_data_flag = false, write_data_flag = false, write_vtk_flag = false;
     int vtk_rate = 0; // 0 = never (the reference takes step % 0 here, Appendix B.2)
     std::string vtk_file;
@@ -161,6 +165,19 @@ class InputFile
         force_neigh_parallel_type = cl.force_neigh_parallel_type;
         output_file = cl.output_file;
         error_file = cl.error_file;
+        if ( cl.dumpbinaryflag && cl.dumpbinary_rate > 0 && cl.dumpbinary_path )
+        {
+            dumpbinaryflag = true;
+            dumpbinary_rate = cl.dumpbinary_rate;
+            dumpbinary_path = cl.dumpbinary_path;
+        }
+        if ( cl.correctnessflag && cl.correctness_rate > 0 && cl.reference_path && cl.correctness_file )
+        {
+            correctnessflag = true;
+            correctness_rate = cl.correctness_rate;
+            reference_path = cl.reference_path;
+            correctness_file = cl.correctness_file;
+        }
         // (sic) computed from the default DENSITY as if it were a lattice constant
         // (inputFile_impl.h:82-83); only sizes the Verlet bounding grid
         comm_ghost_cutoff = std::pow( 4.0 / lattice_constant, 1.0 / 3.0 ) * 20.0;
@@ -326,6 +343,9 @@ class InputFile
         {
             write_data_flag = true;
             output_data_file = arg( 1 );
+            // extension: `write_data FILE precision P` (the reference reads FILE only)
+            if ( words.size() > 3 && words[2] == "precision" )
+                write_data_precision = std::max( 1, std::min( 17, integer( 3 ) ) );
         }
         else if ( key == "dump" )
         {
