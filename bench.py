@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[1] 1 M-atom legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ab", action="store_true", help="skip the nb_group=1 A/B leg")
     ap.add_argument("--cpu-cells", type=int, default=40, help="cpu_baseline sample: cells per dim")
     ap.add_argument("--cutoff", type=float, default=2.5)
     ap.add_argument("--guess", type=int, default=50)
@@ -406,7 +407,9 @@ def main():
         traffic = tr.get(key)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_force_half" if args.half else "k_force_full",
+    group = int(os.environ.get("CBMD_NB_GROUP", "8"))
+    kname = ("k_force_half" if args.half else "k_force_full") + ("_g8" if group == 8 else "")
+    roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": traffic,
                 "bytes_per_launch": fb, "avg_launch_ms": fk_ms / max(fk_n, 1), "launches": fk_n,
@@ -427,6 +430,23 @@ def main():
     extra = {}
     sim.ctx.close()
     del sim
+    if n == 1 and not args.no_ab:
+        # A/B of the pair-sweep shape on the headline workload: one lane per atom (the
+        # round-1 first kernel + tiled table) against the default 8 lanes per atom
+        os.environ["CBMD_NB_GROUP"] = "1"
+        try:
+            s1 = build_sim(args, args.cells, args.half, 1, 0, None, local)
+            s1.setup()
+            m1 = measure_resident(args, s1, args.steps, args.warmup, None, False)
+            f_ms, f_n = m1["timing"]["force_kernel"]
+            extra["A/B nb_group=1 (one lane per atom, tiled table)"] = {
+                "value": s1.N * md_steps / m1["sec"], "unit": UNIT, "atoms": s1.N,
+                "force_kernel_ms": f_ms / max(f_n, 1),
+                "neigh_ms_per_100_md_steps": m1["timing"]["neigh"][0] * 100.0 / md_steps}
+            s1.ctx.close()
+            del s1
+        finally:
+            del os.environ["CBMD_NB_GROUP"]
     if n == 1 and not args.no_extra:
         for half in (False, True):
             a2 = argparse.Namespace(**vars(args))

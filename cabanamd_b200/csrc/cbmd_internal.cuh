@@ -105,8 +105,10 @@ struct cbmd_ctx
     int *perm = nullptr;       // [cap] last sort permutation
     int perm_n = 0;
 
-    // Verlet list, padded + transposed: neighbour n of atom i at nb[n*nb_stride + i]
+    // Verlet list, padded 2-D table; addressing by nb_entry() below
     int nb_half = 0, nb_layout = 0;
+    int nb_group = 8;      // lanes sharing one atom in the pair sweeps (layout of the CURRENT list)
+    int nb_group_next = 8; // option "nb_group" (1 or 8): takes effect at the next build
     int nb_rows = 0;   // row capacity (max_neigh_guess in effect)
     int nb_stride = 0; // >= n_local, multiple of 32
     int nb_n = 0;      // n_local at build time
@@ -324,6 +326,29 @@ __device__ __forceinline__ int cell_coord( double xv, double mn, double rdx, int
 __host__ __device__ __forceinline__ size_t nb_tile_base( int i, int rows )
 {
     return ( (size_t)( i >> 5 ) * (size_t)rows ) * 32 + (size_t)( i & 31 );
+}
+
+// Grouped layout (nb_group == 8): the pair sweeps give every atom 8 lanes that walk 8
+// CONSECUTIVE entries of its row at once (4 atoms per warp).  Entries are stored in quads
+// of atoms: with R8 = ceil(rows/8) chunks per row,
+//   nb[(((i >> 2) * R8 + (n >> 3)) * 32) + (i & 3) * 8 + (n & 7)]
+// so chunk r of the four atoms of a quad is one 128-byte line, lane = (i&3)*8 + (n&7), and a
+// quad's chunks are contiguous.  A 32-atom tile is still one contiguous R8*1024-byte block.
+__host__ __device__ __forceinline__ int nb_chunks( int rows ) { return ( rows + 7 ) >> 3; }
+__host__ __device__ __forceinline__ size_t nb_quad_base( int i, int rows )
+{
+    return ( (size_t)( i >> 2 ) * (size_t)nb_chunks( rows ) ) * 32 + (size_t)( i & 3 ) * 8;
+}
+// element offset of neighbour n of atom i in either layout
+__host__ __device__ __forceinline__ size_t nb_entry( int group, int i, int n, int rows )
+{
+    return group == 8 ? nb_quad_base( i, rows ) + (size_t)( n >> 3 ) * 32 + (size_t)( n & 7 )
+                      : nb_tile_base( i, rows ) + (size_t)n * 32;
+}
+// table elements needed for `stride` (multiple of 32) atoms
+__host__ __device__ __forceinline__ size_t nb_table_size( int group, int stride, int rows )
+{
+    return (size_t)stride * (size_t)( group == 8 ? 8 * nb_chunks( rows ) : rows );
 }
 
 struct GridDesc

@@ -7,10 +7,12 @@
 // evaluated un-contracted, left to right); Full: i != j; Half: i != j and
 // (xj>xi || (xj==xi && (yj>yi || (yj==yi && zj>zi)))); ghost rows are empty.
 //
-// Device layout: padded 2-D table in tiles of 32 atoms — neighbour n of atom i lives
-// at nb[((i>>5)*rows + n)*32 + (i&31)] (nb_tile_base) — so the thread-per-atom force
-// kernel reads the index stream fully coalesced and each warp's rows are one
-// contiguous block.  The CSR view the reference also offers is produced on demand by
+// Device layout: padded 2-D table, addressed by nb_entry() (cbmd_internal.cuh).  Default
+// (nb_group 8): quads of atoms, 8 consecutive entries of each of the 4 atoms per 128-byte
+// line, for the pair sweeps that give every atom 8 lanes.  nb_group 1: tiles of 32 atoms,
+// neighbour n of atom i at nb[((i>>5)*rows + n)*32 + (i&31)], for one lane per atom.  Either
+// way a warp reads its index stream fully coalesced and a tile's rows are one contiguous
+// block.  The CSR view the reference also offers is produced on demand by
 // cbmd_neigh_get.  Row capacity follows Cabana's 2-D policy: start from
 // max_neigh_guess, and if any row overflows rebuild at 1.1 x the observed maximum.
 #include "cbmd_internal.cuh"
@@ -52,7 +54,7 @@ template <bool HALF, int K>
 __device__ __forceinline__ void
 sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const XT &xi, float xr,
              float yr, float zr, int i, float r2lo, float r2hi, float tolx, double rsqr,
-             char *row0, int nb_rows, int &count )
+             char *row0, int nb_rows, int grouped, int &count )
 {
     // i < 0 marks an inactive lane: its r2lo/r2hi are -1 so nothing is ever accepted
     float4 c[K];
@@ -94,9 +96,12 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
 #pragma unroll
     for ( int k = 0; k < K; k++ )
     {
-        // predicated store (no branch): row n of this lane's column is 128 bytes further on
+        // predicated store (no branch).  Tiled layout: entry n of this lane's column is 128
+        // bytes further on; grouped layout: 8 consecutive entries per 128-byte chunk line
         const int st = ( ok[k] && count < nb_rows ) ? 1 : 0;
-        char *dst = row0 + (unsigned long long)(unsigned)count * 128ull;
+        const unsigned off = grouped ? ( ( (unsigned)count >> 3 ) << 7 ) + ( ( (unsigned)count & 7u ) << 2 )
+                                     : (unsigned)count << 7;
+        char *dst = row0 + (unsigned long long)off;
         asm volatile( "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b32 [%0], %1;\n\t}"
                       :
                       : "l"( dst ), "r"( __float_as_int( c[k].w ) ), "r"( st )
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__( NB_THREADS )
     k_neigh_build( const XT *__restrict__ xt, int n_local, GridDesc g,
                    const int *__restrict__ cell_start, const int *__restrict__ cell_atoms,
                    double rsqr, double3 centre, int *__restrict__ nb, int nb_stride, int nb_rows,
-                   int *__restrict__ nb_count, int *__restrict__ d_max )
+                   int nb_group, int *__restrict__ nb_count, int *__restrict__ d_max )
 {
     __shared__ float4 cand[NB_STAGE];
     __shared__ int run_src[9], run_off[10];
@@ -223,7 +228,8 @@ __global__ void __launch_bounds__( NB_THREADS )
             xi = ld_xt( xt + i );
         const float xr = active ? (float)( xi.x - ox ) : 0.f, yr = active ? (float)( xi.y - oy ) : 0.f,
                     zr = active ? (float)( xi.z - oz ) : 0.f;
-        char *const row0 = (char *)( nb + nb_tile_base( active ? i : 0, nb_rows ) );
+        const int grouped = nb_group == 8;
+        char *const row0 = (char *)( nb + nb_entry( nb_group, active ? i : 0, 0, nb_rows ) );
         int count = 0;
 
         for ( int chunk = 0; chunk < total; chunk += NB_STAGE )
@@ -281,10 +287,10 @@ __global__ void __launch_bounds__( NB_THREADS )
                 const float4 *cp = cand + b;
                 for ( int q = 0; q < n4; q++, cp += 4 )
                     sweep_group<HALF, 4>( cp, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx, rsqr, row0,
-                                          nb_rows, count );
+                                          nb_rows, grouped, count );
                 for ( int t = b + 4 * n4; t < e; t++ )
                     sweep_group<HALF, 1>( cand + t, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx, rsqr,
-                                          row0, nb_rows, count );
+                                          row0, nb_rows, grouped, count );
             }
         }
         if ( active )
@@ -298,8 +304,9 @@ __global__ void __launch_bounds__( NB_THREADS )
 }
 
 __global__ void __launch_bounds__( 256 )
-    k_nb_to_csr( const int *__restrict__ nb, int nb_rows, const int *__restrict__ nb_count,
-                 const int64_t *__restrict__ offsets, int n_local, int *__restrict__ csr )
+    k_nb_to_csr( const int *__restrict__ nb, int nb_rows, int nb_group,
+                 const int *__restrict__ nb_count, const int64_t *__restrict__ offsets, int n_local,
+                 int *__restrict__ csr )
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if ( i >= n_local )
@@ -307,7 +314,7 @@ __global__ void __launch_bounds__( 256 )
     const int c = nb_count[i];
     const int64_t o = offsets[i];
     for ( int n = 0; n < c; n++ )
-        csr[o + n] = nb[nb_tile_base( i, nb_rows ) + (size_t)n * 32];
+        csr[o + n] = nb[nb_entry( nb_group, i, n, nb_rows )];
 }
 
 // ---------------------------------------------------------------------------
@@ -424,6 +431,7 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
     cbmd_build_cell_lists_grid( ctx, g, 0, n_total );
 
     ctx->nb_half = half ? 1 : 0;
+    ctx->nb_group = ctx->nb_group_next;
     ctx->nb_layout = layout;
     ctx->nb_rcut = rcut;
     ctx->nb_n = n_local;
@@ -440,7 +448,7 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
     int observed = 0;
     for ( int attempt = 0; attempt < 3; attempt++ )
     {
-        const size_t need = (size_t)rows * (size_t)( stride > 0 ? stride : 32 );
+        const size_t need = nb_table_size( ctx->nb_group, stride > 0 ? stride : 32, rows );
         if ( need > ctx->nb_alloc )
         {
             if ( ctx->nb )
@@ -461,11 +469,11 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
             if ( half )
                 k_neigh_build<true><<<blocks, NB_THREADS, 0, s>>>(
                     ctx->xt, n_local, g, ctx->cell_start, ctx->cell_atoms, rsqr, centre, ctx->nb,
-                    stride, rows, ctx->nb_count, d_max );
+                    stride, rows, ctx->nb_group, ctx->nb_count, d_max );
             else
                 k_neigh_build<false><<<blocks, NB_THREADS, 0, s>>>(
                     ctx->xt, n_local, g, ctx->cell_start, ctx->cell_atoms, rsqr, centre, ctx->nb,
-                    stride, rows, ctx->nb_count, d_max );
+                    stride, rows, ctx->nb_group, ctx->nb_count, d_max );
             CBMD_LAUNCH_CHECK( ctx );
         }
         // NeighborList<>::maxNeighbor (neighbor_verlet.h:58-59)
@@ -520,8 +528,8 @@ extern "C" int cbmd_neigh_get( cbmd_ctx *ctx, int *counts, int64_t *offsets, int
         int *d_csr = (int *)( st + ob );
         CBMD_CUDA( cudaMemcpyAsync( d_off, ho.data(), (size_t)( n_local + 1 ) * sizeof( int64_t ),
                                     cudaMemcpyHostToDevice, s ) );
-        k_nb_to_csr<<<div_up( n_local, 256 ), 256, 0, s>>>( ctx->nb, ctx->nb_rows, ctx->nb_count,
-                                                            d_off, n_local, d_csr );
+        k_nb_to_csr<<<div_up( n_local, 256 ), 256, 0, s>>>( ctx->nb, ctx->nb_rows, ctx->nb_group,
+                                                            ctx->nb_count, d_off, n_local, d_csr );
         CBMD_LAUNCH_CHECK( ctx );
         CBMD_CUDA( cudaMemcpyAsync( neighbors, d_csr, (size_t)ho[n_local] * sizeof( int ),
                                     cudaMemcpyDeviceToHost, s ) );

@@ -214,6 +214,8 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
         ctx->device = device;
         if ( const char *e = getenv( "CBMD_OVERLAP" ) ) // A/B switch for measurements
             ctx->overlap = atoi( e );
+        if ( const char *e = getenv( "CBMD_NB_GROUP" ) ) // A/B switch: 1 = one lane per atom
+            ctx->nb_group_next = atoi( e ) == 1 ? 1 : 8;
         CBMD_CUDA( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
         {
             int lo = 0, hi = 0; // comm stream gets the highest priority so its small kernels
@@ -311,6 +313,13 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
         ctx->force_variant = (int)value;
     else if ( n == "overlap" )
         ctx->overlap = (int)value;
+    else if ( n == "nb_group" )
+    {
+        // lanes per atom in the pair sweeps + matching table layout; next cbmd_neigh_build
+        if ( (int)value != 1 && (int)value != 8 )
+            throw CbmdError( "nb_group must be 1 or 8" );
+        ctx->nb_group_next = (int)value;
+    }
     else
         throw CbmdError( "unknown option: " + n );
     CBMD_API_END
