@@ -107,8 +107,8 @@ struct cbmd_ctx
 
     // Verlet list, padded 2-D table; addressing by nb_entry() below
     int nb_half = 0, nb_layout = 0;
-    int nb_group = 8;      // lanes sharing one atom in the pair sweeps (layout of the CURRENT list)
-    int nb_group_next = 8; // option "nb_group" (1 or 8): takes effect at the next build
+    int nb_group = 1;      // lanes sharing one atom in the pair sweeps (layout of the CURRENT list)
+    int nb_group_next = 1; // option "nb_group" (1 or 8): takes effect at the next build
     int nb_rows = 0;   // row capacity (max_neigh_guess in effect)
     int nb_stride = 0; // >= n_local, multiple of 32
     int nb_n = 0;      // n_local at build time
@@ -328,7 +328,7 @@ __host__ __device__ __forceinline__ size_t nb_tile_base( int i, int rows )
     return ( (size_t)( i >> 5 ) * (size_t)rows ) * 32 + (size_t)( i & 31 );
 }
 
-// Grouped layout (nb_group == 8): the pair sweeps give every atom 8 lanes that walk 8
+// Grouped layout (option nb_group == 8, an A/B alternative): the pair sweeps give every atom 8 lanes that walk 8
 // CONSECUTIVE entries of its row at once (4 atoms per warp).  Entries are stored in quads
 // of atoms: with R8 = ceil(rows/8) chunks per row,
 //   nb[(((i >> 2) * R8 + (n >> 3)) * 32) + (i & 3) * 8 + (n & 7)]

@@ -8,11 +8,11 @@
 // (xj>xi || (xj==xi && (yj>yi || (yj==yi && zj>zi)))); ghost rows are empty.
 //
 // Device layout: padded 2-D table, addressed by nb_entry() (cbmd_internal.cuh).  Default
-// (nb_group 8): quads of atoms, 8 consecutive entries of each of the 4 atoms per 128-byte
-// line, for the pair sweeps that give every atom 8 lanes.  nb_group 1: tiles of 32 atoms,
-// neighbour n of atom i at nb[((i>>5)*rows + n)*32 + (i&31)], for one lane per atom.  Either
-// way a warp reads its index stream fully coalesced and a tile's rows are one contiguous
-// block.  The CSR view the reference also offers is produced on demand by
+// (nb_group 1): tiles of 32 atoms, neighbour n of atom i at nb[((i>>5)*rows + n)*32 + (i&31)],
+// for the one-lane-per-atom sweeps.  Option nb_group 8: quads of atoms, 8 consecutive entries
+// of each of the 4 atoms per 128-byte line, for the sweeps that give every atom 8 lanes.
+// Either way a warp reads its index stream fully coalesced and a tile's rows are one
+// contiguous block.  The CSR view the reference also offers is produced on demand by
 // cbmd_neigh_get.  Row capacity follows Cabana's 2-D policy: start from
 // max_neigh_guess, and if any row overflows rebuild at 1.1 x the observed maximum.
 #include "cbmd_internal.cuh"

@@ -214,8 +214,8 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
         ctx->device = device;
         if ( const char *e = getenv( "CBMD_OVERLAP" ) ) // A/B switch for measurements
             ctx->overlap = atoi( e );
-        if ( const char *e = getenv( "CBMD_NB_GROUP" ) ) // A/B switch: 1 = one lane per atom
-            ctx->nb_group_next = atoi( e ) == 1 ? 1 : 8;
+        if ( const char *e = getenv( "CBMD_NB_GROUP" ) ) // A/B switch: 8 = eight lanes per atom
+            ctx->nb_group_next = atoi( e ) == 8 ? 8 : 1;
         CBMD_CUDA( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
         {
             int lo = 0, hi = 0; // comm stream gets the highest priority so its small kernels

@@ -107,3 +107,31 @@ for kind in ("cell", "cell+sub2", "grid1.4", "morton1.4", "morton0.7", "colz1.4"
     for G in (4, 8, 16, 32):
         l, r = measure_group(kind, G)
         print(f"{kind:12s} G={G:2d}    lines/atom {l:6.1f}  warp-rows/atom {r:5.2f}")
+
+print("\nquarter-warp model (LDG.256: one wavefront per distinct 128-byte line among each aligned group of 8 lanes)")
+def measure_quarter(kind, natoms=4000):
+    perm = order_key(kind)
+    inv = np.empty(n, int); inv[perm] = np.arange(n)
+    a, b = inv[pairs[:, 0]], inv[pairs[:, 1]]
+    src = np.concatenate([a, b]); dst = np.concatenate([b, a])
+    o = np.lexsort((dst, src)); src, dst = src[o], dst[o]
+    off = np.searchsorted(src, np.arange(n + 1))
+    # (1) one lane per atom: 8 consecutive atoms, k-th entries
+    t1 = r1 = 0
+    for t in rng.choice(n // 8, size=natoms // 8, replace=False):
+        ls = [dst[off[i]:off[i + 1]] // APL for i in range(8 * t, 8 * t + 8)]
+        R = max(len(l) for l in ls)
+        for k in range(R):
+            t1 += len({int(l[k]) for l in ls if k < len(l)})
+        r1 += sum(len(l) for l in ls)
+    # (2) 8 lanes per atom: 8 consecutive entries of one atom
+    t8 = r8 = 0
+    for i in rng.choice(n, size=natoms, replace=False):
+        l = dst[off[i]:off[i + 1]] // APL
+        for k in range(0, len(l), 8):
+            t8 += len(set(l[k:k + 8].tolist()))
+        r8 += len(l)
+    return t1 / r1, t8 / r8
+for kind in ("cell", "cell+sub2", "cell+sub3", "cell+zsort", "grid1.4", "grid0.93", "morton1.4", "morton0.7", "colz1.4", "colz0.93", "colz0.7"):
+    w1, w8 = measure_quarter(kind)
+    print(f"{kind:12s} wavefronts per pair: lane/atom {w1:5.3f} (x32 = {32*w1:5.1f}/request)   8 lanes/atom {w8:5.3f} (x32 = {32*w8:5.1f}/request)")

@@ -146,7 +146,7 @@ def test_binning_matches_oracle(cb):
 def test_force_energy_on_oracle_state(cb, half, group):
     """Same atoms (owned + ghosts from the oracle's 6-phase build): neighbour sets
     bit-exact, forces <= 1e-10 relative, energy to round-off.  Both table layouts /
-    sweep shapes: 8 lanes per atom (default) and one lane per atom."""
+    sweep shapes: one lane per atom (default) and 8 lanes per atom."""
     s = melted_state((10, 10, 10), 60, half)
     d = s.get()
     n, ng = d["n_local"], d["n_ghost"]
