@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[1] 1 M-atom legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-ab", action="store_true", help="skip the nb_group=8 A/B leg")
+    ap.add_argument("--no-ab", action="store_true", help="skip the A/B legs (gather=0, nb_group=8)")
     ap.add_argument("--cpu-cells", type=int, default=40, help="cpu_baseline sample: cells per dim")
     ap.add_argument("--cutoff", type=float, default=2.5)
     ap.add_argument("--guess", type=int, default=50)
@@ -408,7 +408,9 @@ def main():
     except Exception:
         pass
     group = int(os.environ.get("CBMD_NB_GROUP", "1"))
-    kname = ("k_force_half" if args.half else "k_force_full") + ("_g8" if group == 8 else "")
+    gather = int(os.environ.get("CBMD_GATHER", "1"))
+    kname = ("k_force_half" if args.half else "k_force_full") + (
+        "_g8" if group == 8 else ("_tex" if gather == 1 and not args.half else ""))
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": traffic,
@@ -431,22 +433,26 @@ def main():
     sim.ctx.close()
     del sim
     if n == 1 and not args.no_ab:
-        # A/B of the pair-sweep shape on the headline workload: 8 lanes per atom over the
-        # quad-grouped table against the default one lane per atom
-        os.environ["CBMD_NB_GROUP"] = "8"
-        try:
-            s1 = build_sim(args, args.cells, args.half, 1, 0, None, local)
-            s1.setup()
-            m1 = measure_resident(args, s1, args.steps, args.warmup, None, False)
-            f_ms, f_n = m1["timing"]["force_kernel"]
-            extra["A/B nb_group=8 (eight lanes per atom, quad-grouped table)"] = {
-                "value": s1.N * md_steps / m1["sec"], "unit": UNIT, "atoms": s1.N,
-                "force_kernel_ms": f_ms / max(f_n, 1),
-                "neigh_ms_per_100_md_steps": m1["timing"]["neigh"][0] * 100.0 / md_steps}
-            s1.ctx.close()
-            del s1
-        finally:
-            del os.environ["CBMD_NB_GROUP"]
+        # A/B of the force kernel's gather path / sweep shape on the headline workload
+        # (DESIGN.md 3.1): 32-byte records by LDG.256 (no texture path), and 8 lanes per atom
+        for label, env in (("A/B gather=0 (32-byte records, LDG.256 only)", {"CBMD_GATHER": "0"}),
+                           ("A/B nb_group=8 (eight lanes per atom, quad-grouped table)",
+                            {"CBMD_NB_GROUP": "8"})):
+            os.environ.update(env)
+            try:
+                s1 = build_sim(args, args.cells, args.half, 1, 0, None, local)
+                s1.setup()
+                m1 = measure_resident(args, s1, args.steps, args.warmup, None, False)
+                f_ms, f_n = m1["timing"]["force_kernel"]
+                extra[label] = {
+                    "value": s1.N * md_steps / m1["sec"], "unit": UNIT, "atoms": s1.N,
+                    "force_kernel_ms": f_ms / max(f_n, 1),
+                    "force_bucket_ms_per_100_md_steps": m1["timing"]["force"][0] * 100.0 / md_steps}
+                s1.ctx.close()
+                del s1
+            finally:
+                for k in env:
+                    del os.environ[k]
     if n == 1 and not args.no_extra:
         for half in (False, True):
             a2 = argparse.Namespace(**vars(args))

@@ -218,7 +218,7 @@ extern "C" int cbmd_bin_sort( cbmd_ctx *ctx, double dx, double dy, double dz, in
     CBMD_REQUIRE( ctx->have_domain, "cbmd_set_domain must be called before cbmd_bin_sort" );
     CBMD_REQUIRE( dx > 0 && dy > 0 && dz > 0, "bin sizes must be positive" );
     cbmd_materialize_zero_force( ctx );
-    ctx->epoch++;
+    cbmd_bump_epoch( ctx, true, true );
     const double din[3] = { dx, dy, dz };
     GridDesc g;
     cbmd_binning_grid( ctx, din, halo_depth, ctx->nbin, ctx->bmin, ctx->bmax, g );

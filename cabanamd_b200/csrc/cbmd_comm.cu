@@ -283,7 +283,7 @@ extern "C" int cbmd_exchange( cbmd_ctx *ctx, int *n_sent_global )
     TimedRegion timed__( ctx, CBMD_T_COMM );
     CBMD_REQUIRE( ctx->have_domain, "cbmd_set_domain must be called before cbmd_exchange" );
     cbmd_materialize_zero_force( ctx );
-    ctx->epoch++;
+    cbmd_bump_epoch( ctx, true, true );
     cudaStream_t s = ctx->stream;
     // system->resize(N_local): ghosts are dropped (comm_mpi_impl.h:196-197)
     ctx->n_ghost = 0;
@@ -432,7 +432,7 @@ extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
     CBMD_REQUIRE( ctx->have_domain, "cbmd_set_domain must be called before cbmd_exchange_halo" );
     CBMD_REQUIRE( comm_depth > 0, "comm depth must be positive" );
     cbmd_materialize_zero_force( ctx );
-    ctx->epoch++;
+    cbmd_bump_epoch( ctx, true, true );
     cudaStream_t s = ctx->stream;
     ctx->comm_depth = comm_depth;
     ctx->n_ghost = 0;
@@ -544,7 +544,8 @@ extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
 __global__ void __launch_bounds__( 256 )
     k_halo_update_flat( XT *__restrict__ xt, int n_local, int n_ghost,
                         const int *__restrict__ owner, const unsigned char *__restrict__ image,
-                        double Lx, double Ly, double Lz )
+                        double Lx, double Ly, double Lz, double2 *__restrict__ xy,
+                        double *__restrict__ zs )
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if ( g >= n_ghost )
@@ -559,6 +560,11 @@ __global__ void __launch_bounds__( 256 )
     if ( iz )
         r.z += ( iz == 1u ? Lz : -Lz );
     xt[n_local + g] = r;
+    if ( xy ) // split mirror for the texture-assisted force gather (cbmd_force.cu)
+    {
+        xy[n_local + g] = make_double2( r.x, r.y );
+        zs[n_local + g] = r.z;
+    }
 }
 
 __global__ void __launch_bounds__( 256 )
@@ -584,15 +590,19 @@ extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
     TimedRegion timed__( ctx, CBMD_T_COMM );
     CBMD_REQUIRE( ctx->have_halo, "cbmd_exchange_halo must be called before cbmd_update_halo" );
     cbmd_join_halo( ctx ); // a previous refresh nobody consumed
-    ctx->epoch++;
+    cbmd_bump_epoch( ctx, false, true );
     if ( ctx->n_ghost == 0 )
         return 0;
     if ( ctx->flat_halo_ok )
     {
+        // the ghosts are images of owned atoms: the copy is only right if those are current
+        const bool live = cbmd_mirror_live( ctx );
         k_halo_update_flat<<<div_up( ctx->n_ghost, 256 ), 256, 0, ctx->stream>>>(
             ctx->xt, ctx->n_local, ctx->n_ghost, ctx->ghost_owner, ctx->ghost_image, ctx->gext[0],
-            ctx->gext[1], ctx->gext[2] );
+            ctx->gext[1], ctx->gext[2], live ? ctx->xy : nullptr, live ? ctx->zs : nullptr );
         CBMD_LAUNCH_CHECK( ctx );
+        if ( live )
+            ctx->mirror_ghost_epoch = ctx->epoch;
         return 0;
     }
     // multi-rank: the six dependent phases run on the comm stream so the force kernel can

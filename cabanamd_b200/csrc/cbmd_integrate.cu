@@ -12,7 +12,8 @@
 
 __global__ void __launch_bounds__( 256 )
     k_integrate_initial( XT *__restrict__ xt, double *__restrict__ v, const double *__restrict__ f,
-                         int cap, int n, const __grid_constant__ MassTable mt, double dtv )
+                         int cap, int n, const __grid_constant__ MassTable mt, double dtv,
+                         double2 *__restrict__ xy, double *__restrict__ zs )
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if ( i >= n )
@@ -31,6 +32,11 @@ __global__ void __launch_bounds__( 256 )
     v[(size_t)cap + i] = vy;
     v[2 * (size_t)cap + i] = vz;
     xt[i] = r;
+    if ( xy ) // split mirror for the texture-assisted force gather (cbmd_force.cu)
+    {
+        xy[i] = make_double2( r.x, r.y );
+        zs[i] = r.z;
+    }
 }
 
 __global__ void __launch_bounds__( 256 )
@@ -53,7 +59,8 @@ __global__ void __launch_bounds__( 256 )
 __global__ void __launch_bounds__( 256 )
     k_integrate_final_initial( XT *__restrict__ xt, double *__restrict__ v,
                                const double *__restrict__ f, int cap, int n,
-                               const __grid_constant__ MassTable mt, double dtv )
+                               const __grid_constant__ MassTable mt, double dtv,
+                               double2 *__restrict__ xy, double *__restrict__ zs )
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if ( i >= n )
@@ -73,6 +80,11 @@ __global__ void __launch_bounds__( 256 )
     v[(size_t)cap + i] = vy;
     v[2 * (size_t)cap + i] = vz;
     xt[i] = r;
+    if ( xy )
+    {
+        xy[i] = make_double2( r.x, r.y );
+        zs[i] = r.z;
+    }
 }
 
 void cbmd_materialize_final( cbmd_ctx *ctx )
@@ -96,19 +108,25 @@ extern "C" int cbmd_integrate_initial( cbmd_ctx *ctx )
     cbmd_join_halo( ctx );
     TimedRegion timed__( ctx, CBMD_T_INTEGRATE );
     cbmd_materialize_zero_force( ctx );
-    ctx->epoch++;
+    cbmd_bump_epoch( ctx, true, false );
     const int n = ctx->n_local;
     const bool fused = ctx->final_pending;
     ctx->final_pending = false;
     if ( n > 0 )
     {
+        // every owned position is rewritten here: keep the force kernel's split mirror current
+        const bool live = cbmd_mirror_live( ctx );
+        double2 *xy = live ? ctx->xy : nullptr;
+        double *zs = live ? ctx->zs : nullptr;
         if ( fused )
             k_integrate_final_initial<<<div_up( n, 256 ), 256, 0, ctx->stream>>>(
-                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt );
+                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt, xy, zs );
         else
             k_integrate_initial<<<div_up( n, 256 ), 256, 0, ctx->stream>>>(
-                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt );
+                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt, xy, zs );
         CBMD_LAUNCH_CHECK( ctx );
+        if ( live )
+            ctx->mirror_owned_epoch = ctx->epoch;
     }
     CBMD_API_END
 }

@@ -78,6 +78,18 @@ struct cbmd_ctx
     double *f = nullptr, *f_alt = nullptr; // SoA [3][cap]
     int *id = nullptr, *id_alt = nullptr;
     double *q = nullptr, *q_alt = nullptr;
+    // split mirror of the positions for the texture-assisted gather of the single-type
+    // full-list force kernel (cbmd_force.cu): x,y packed as double2 (LDG.128 through the LSU
+    // pipe), z as a plain array read through the TEX path (8-byte texels)
+    double2 *xy = nullptr;
+    double *zs = nullptr;
+    cudaTextureObject_t tex_z = 0;
+    int mirror_cap = 0;
+    // value of `epoch` at which the owned / ghost part of the mirror was last consistent with
+    // xt; the integrator and the one-rank halo refresh write the mirror themselves, anything
+    // else that moves atoms leaves it stale and cbmd_force_lj re-splits that part
+    uint64_t mirror_owned_epoch = 0, mirror_ghost_epoch = 0;
+    int gather_mode = 1; // option "gather": 0 = 32-byte records by LDG.256, 1 = xy LDG.128 + z TEX
     bool f_zero_pending = false; // deferred deep_copy(f,0): fused into the full-list force kernel
     // deferred Integrator::final_integrate: when the next call is initial_integrate the two
     // half kicks and the drift run as ONE streaming kernel (same roundings, 43 % less traffic);
@@ -285,6 +297,24 @@ inline void cbmd_join_halo( cbmd_ctx *ctx )
 void *cbmd_scratch( cbmd_ctx *ctx, size_t bytes );
 void cbmd_materialize_zero_force( cbmd_ctx *ctx );
 void cbmd_materialize_final( cbmd_ctx *ctx );
+
+// every call that moves atoms or rebuilds the list bumps the epoch; the mirror stays valid
+// for the parts the call did not touch
+inline void cbmd_bump_epoch( cbmd_ctx *ctx, bool owned_changed, bool ghosts_changed )
+{
+    const bool o = ctx->mirror_owned_epoch == ctx->epoch && !owned_changed;
+    const bool g = ctx->mirror_ghost_epoch == ctx->epoch && !ghosts_changed;
+    ctx->epoch++;
+    if ( o )
+        ctx->mirror_owned_epoch = ctx->epoch;
+    if ( g )
+        ctx->mirror_ghost_epoch = ctx->epoch;
+}
+// the split mirror is allocated for the current capacity and in use
+inline bool cbmd_mirror_live( const cbmd_ctx *ctx )
+{
+    return ctx->gather_mode == 1 && ctx->xy != nullptr && ctx->mirror_cap == ctx->cap;
+}
 void cbmd_exclusive_scan_int( cbmd_ctx *ctx, int *data, int n ); // in place, data[n] = total
 
 // ---------------------------------------------------------------------------

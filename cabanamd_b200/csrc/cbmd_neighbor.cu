@@ -412,7 +412,7 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
     CBMD_REQUIRE( layout == CBMD_LAYOUT_2D || layout == CBMD_LAYOUT_CSR, "unknown list layout" );
     const int n_local = ctx->n_local, n_total = ctx->n_local + ctx->n_ghost;
     cudaStream_t s = ctx->stream;
-    ctx->epoch++;
+    cbmd_bump_epoch( ctx, false, false );
 
     // cell grid of size >= rcut around the owned box; atoms outside are clamped into
     // the edge cells, which keeps |cell(i)-cell(j)| <= 1 for every pair within rcut.

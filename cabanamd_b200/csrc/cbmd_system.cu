@@ -214,6 +214,8 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
         ctx->device = device;
         if ( const char *e = getenv( "CBMD_OVERLAP" ) ) // A/B switch for measurements
             ctx->overlap = atoi( e );
+        if ( const char *e = getenv( "CBMD_GATHER" ) ) // A/B switch: 0 = 32-byte records by LDG.256
+            ctx->gather_mode = atoi( e ) == 0 ? 0 : 1;
         if ( const char *e = getenv( "CBMD_NB_GROUP" ) ) // A/B switch: 8 = eight lanes per atom
             ctx->nb_group_next = atoi( e ) == 8 ? 8 : 1;
         CBMD_CUDA( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
@@ -266,6 +268,12 @@ extern "C" int cbmd_destroy( cbmd_ctx *ctx )
         cudaEventDestroy( ctx->ev_boundary );
         cudaEventDestroy( ctx->ev_fready );
     }
+    if ( ctx->tex_z )
+        cudaDestroyTextureObject( ctx->tex_z );
+    if ( ctx->xy )
+        cudaFree( ctx->xy );
+    if ( ctx->zs )
+        cudaFree( ctx->zs );
     void *ptrs[] = { ctx->xt,         ctx->xt_alt,      ctx->v,          ctx->v_alt,
                      ctx->f,          ctx->f_alt,       ctx->id,         ctx->id_alt,
                      ctx->q,          ctx->q_alt,       ctx->cell_start, ctx->cell_cursor,
@@ -313,6 +321,12 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
         ctx->force_variant = (int)value;
     else if ( n == "overlap" )
         ctx->overlap = (int)value;
+    else if ( n == "gather" )
+    {
+        if ( (int)value != 0 && (int)value != 1 )
+            throw CbmdError( "gather must be 0 (LDG.256 records) or 1 (xy LDG.128 + z TEX)" );
+        ctx->gather_mode = (int)value;
+    }
     else if ( n == "nb_group" )
     {
         // lanes per atom in the pair sweeps + matching table layout; next cbmd_neigh_build
@@ -492,7 +506,7 @@ extern "C" int cbmd_set_atoms( cbmd_ctx *ctx, int n_local, const double *x, cons
     CBMD_REQUIRE( n_local >= 0, "negative atom count" );
     ctx->n_local = 0;
     ctx->n_ghost = 0;
-    ctx->epoch++;
+    cbmd_bump_epoch( ctx, true, true );
     cbmd_ensure_capacity( ctx, n_local );
     ctx->f_zero_pending = false;
     upload_rows( ctx, 0, n_local, x, v, f, type, id, q, 1 );
@@ -509,7 +523,7 @@ extern "C" int cbmd_append_ghosts( cbmd_ctx *ctx, int n, const double *x, const 
     CBMD_API_BEGIN
     CBMD_REQUIRE( n >= 0, "negative ghost count" );
     cbmd_materialize_zero_force( ctx );
-    ctx->epoch++;
+    cbmd_bump_epoch( ctx, true, true );
     const int first = ctx->n_local + ctx->n_ghost;
     cbmd_ensure_capacity( ctx, first + n );
     upload_rows( ctx, first, n, x, nullptr, nullptr, type, id, nullptr, first + 1 );

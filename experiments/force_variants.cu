@@ -25,6 +25,10 @@
         }                                                                                         \
     } while ( 0 )
 
+// the product's tiled Verlet table: neighbour k of atom i at nb[((i>>5)*rows + k)*32 + (i&31)];
+// every kernel's `stride` argument is the row capacity of that table
+#define TB( i, rows ) ( ( (size_t)( ( i ) >> 5 ) * (size_t)( rows ) ) * 32 + (size_t)( ( i ) & 31 ) )
+
 struct alignas( 32 ) XT
 {
     double x, y, z;
@@ -91,11 +95,11 @@ __global__ void __launch_bounds__( 128 )
     const XT xi = ld_xt( xt + i );
     double fx = 0, fy = 0, fz = 0;
     const int c = cnt[i];
-    const int *p = nb + i;
+    const int *p = nb + TB( i, stride );
 #pragma unroll 4
     for ( int k = 0; k < c; k++ )
     {
-        const int j = __ldg( p + (size_t)k * stride );
+        const int j = __ldg( p + k * 32 );
         const XT xj = ld_xt( xt + j );
         const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
         LJ_BODY( rcp5, rsq < cutsq )
@@ -116,11 +120,11 @@ __global__ void __launch_bounds__( 128 )
     const XT xi = ld_xt( xt + i );
     double fx = 0, fy = 0, fz = 0;
     const int c = cnt[i];
-    const int *p = nb + i;
+    const int *p = nb + TB( i, stride );
 #pragma unroll 4
     for ( int k = 0; k < c; k++ )
     {
-        const int j = __ldg( p + (size_t)k * stride );
+        const int j = __ldg( p + k * 32 );
         const XT xj = ld_xt( xt + j );
         const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
         LJ_BODY( rcp3, lt_pos( rsq, cutsq ) )
@@ -143,11 +147,11 @@ __global__ void __launch_bounds__( 128 )
     const double xi = x[i], yi = y[i], zi = z[i];
     double fx = 0, fy = 0, fz = 0;
     const int c = cnt[i];
-    const int *p = nb + i;
+    const int *p = nb + TB( i, stride );
 #pragma unroll UNROLL
     for ( int k = 0; k < c; k++ )
     {
-        const int j = __ldg( p + (size_t)k * stride );
+        const int j = __ldg( p + k * 32 );
         const double dx = xi - __ldg( x + j ), dy = yi - __ldg( y + j ), dz = zi - __ldg( z + j );
         LJ_BODY( rcp3, lt_pos( rsq, cutsq ) )
     }
@@ -167,11 +171,11 @@ __global__ void __launch_bounds__( 128 )
     const XT xi = ld_xt( xt + i );
     double fx = 0, fy = 0, fz = 0;
     const int c = cnt[i];
-    const int *p = nb + i;
+    const int *p = nb + TB( i, stride );
 #pragma unroll 4
     for ( int k = 0; k < c; k++ )
     {
-        const int j = __ldg( p + (size_t)k * stride );
+        const int j = __ldg( p + k * 32 );
         const double2 xy = __ldg( (const double2 *)( xt + j ) );
         const double zz = __ldg( &xt[j].z );
         const double dx = xi.x - xy.x, dy = xi.y - xy.y, dz = xi.z - zz;
@@ -193,11 +197,11 @@ __global__ void __launch_bounds__( 128 )
     const double xi = x3[3 * (size_t)i], yi = x3[3 * (size_t)i + 1], zi = x3[3 * (size_t)i + 2];
     double fx = 0, fy = 0, fz = 0;
     const int c = cnt[i];
-    const int *p = nb + i;
+    const int *p = nb + TB( i, stride );
 #pragma unroll 4
     for ( int k = 0; k < c; k++ )
     {
-        const int j = __ldg( p + (size_t)k * stride );
+        const int j = __ldg( p + k * 32 );
         const double *q = x3 + 3 * (size_t)j;
         const double dx = xi - __ldg( q ), dy = yi - __ldg( q + 1 ), dz = zi - __ldg( q + 2 );
         LJ_BODY( rcp3, lt_pos( rsq, cutsq ) )
@@ -205,6 +209,183 @@ __global__ void __launch_bounds__( 128 )
     f[i] = fx;
     f[(size_t)cap + i] = fy;
     f[2 * (size_t)cap + i] = fz;
+}
+
+
+// ---- texture-path gathers: the TEX front end of L1 instead of (or next to) the LSU pipe.
+// MODE 0: every neighbour through two tex1Dfetch<int4>; MODE 1: odd neighbours through TEX,
+// even ones through LDG.256; MODE 2: one in four through TEX.
+__device__ __forceinline__ void tex_xt( cudaTextureObject_t tex, int j, double &x, double &y, double &z )
+{
+    const int4 a = tex1Dfetch<int4>( tex, 2 * j );
+    const int4 b = tex1Dfetch<int4>( tex, 2 * j + 1 );
+    x = __hiloint2double( a.y, a.x );
+    y = __hiloint2double( a.w, a.z );
+    z = __hiloint2double( b.y, b.x );
+}
+template <int MODE>
+__global__ void __launch_bounds__( 128 )
+    k_tex( const XT *__restrict__ xt, cudaTextureObject_t tex, const int *__restrict__ nb,
+           const int *__restrict__ cnt, int stride, int n, double *__restrict__ f, int cap, double lj1,
+           double lj2, double cutsq )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    const XT xi = ld_xt( xt + i );
+    double fx = 0, fy = 0, fz = 0;
+    const int c = cnt[i];
+    const int *p = nb + TB( i, stride );
+#pragma unroll 4
+    for ( int k = 0; k < c; k++ )
+    {
+        const int j = __ldg( p + k * 32 );
+        double xj, yj, zj;
+        const bool via_tex = MODE == 0 || ( MODE == 1 && ( k & 1 ) ) || ( MODE == 2 && ( k & 3 ) == 3 );
+        if ( via_tex )
+            tex_xt( tex, j, xj, yj, zj );
+        else
+        {
+            const XT t = ld_xt( xt + j );
+            xj = t.x;
+            yj = t.y;
+            zj = t.z;
+        }
+        const double dx = xi.x - xj, dy = xi.y - yj, dz = xi.z - zj;
+        LJ_BODY( rcp5, rsq < cutsq )
+    }
+    f[i] = fx;
+    f[(size_t)cap + i] = fy;
+    f[2 * (size_t)cap + i] = fz;
+}
+
+
+// more TEX mixes.  FETCH 0: two int4 texels (32 B); 1: three int2 texels (24 B) of the same AoS
+// record; 2: one int4 texel (x,y) through TEX + z through LDG.64 from the SoA z array.
+// TEX_NUM of every TEX_DEN neighbours go through TEX, the rest through LDG.256.
+template <int FETCH, int TEX_NUM, int TEX_DEN, int U>
+__global__ void __launch_bounds__( 128 )
+    k_tex2( const XT *__restrict__ xt, cudaTextureObject_t tex4, cudaTextureObject_t tex2,
+            const double *__restrict__ zs, cudaTextureObject_t texz, const double2 *__restrict__ xy,
+            const int *__restrict__ nb, const int *__restrict__ cnt,
+            int stride, int n, double *__restrict__ f, int cap, double lj1, double lj2, double cutsq )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    const XT xi = ld_xt( xt + i );
+    double fx = 0, fy = 0, fz = 0;
+    const int c = cnt[i];
+    const int *p = nb + TB( i, stride );
+#pragma unroll( U & 15 )
+    for ( int k = 0; k < c; k++ )
+    {
+        const int j = __ldg( p + k * 32 );
+        double xj, yj, zj;
+        if ( ( k % TEX_DEN ) < TEX_NUM )
+        {
+            if ( FETCH == 5 || ( FETCH == 6 && ( k & 1 ) ) )
+            { // x,y through TEX from the PACKED xy array (texel j), z through LDG.64
+                const int4 a = tex1Dfetch<int4>( tex2, j ); // tex2 is bound to xy as int4 in this mode
+                xj = __hiloint2double( a.y, a.x );
+                yj = __hiloint2double( a.w, a.z );
+                zj = __ldg( zs + j );
+            }
+            else if ( FETCH == 3 || FETCH == 6 )
+            { // x,y through LDG.128 from the packed xy array, z through TEX (8 B texel)
+                const double2 t = __ldg( xy + j );
+                const int2 d = tex1Dfetch<int2>( texz, j );
+                xj = t.x;
+                yj = t.y;
+                zj = __hiloint2double( d.y, d.x );
+            }
+            else if ( FETCH == 4 )
+            { // x,y through TEX (16 B texel), z through TEX (8 B texel of the SoA z array)
+                const int4 a = tex1Dfetch<int4>( tex4, 2 * j );
+                const int2 d = tex1Dfetch<int2>( texz, j );
+                xj = __hiloint2double( a.y, a.x );
+                yj = __hiloint2double( a.w, a.z );
+                zj = __hiloint2double( d.y, d.x );
+            }
+            else if ( FETCH == 0 )
+                tex_xt( tex4, j, xj, yj, zj );
+            else if ( FETCH == 1 )
+            {
+                const int2 a = tex1Dfetch<int2>( tex2, 4 * j );
+                const int2 b = tex1Dfetch<int2>( tex2, 4 * j + 1 );
+                const int2 d = tex1Dfetch<int2>( tex2, 4 * j + 2 );
+                xj = __hiloint2double( a.y, a.x );
+                yj = __hiloint2double( b.y, b.x );
+                zj = __hiloint2double( d.y, d.x );
+            }
+            else
+            {
+                const int4 a = tex1Dfetch<int4>( tex4, 2 * j );
+                xj = __hiloint2double( a.y, a.x );
+                yj = __hiloint2double( a.w, a.z );
+                zj = __ldg( zs + j );
+            }
+        }
+        else
+        {
+            const XT t = ld_xt( xt + j );
+            xj = t.x;
+            yj = t.y;
+            zj = t.z;
+        }
+        const double dx = xi.x - xj, dy = xi.y - yj, dz = xi.z - zj;
+        LJ_BODY( rcp5, rsq < cutsq )
+    }
+    f[i] = fx;
+    f[(size_t)cap + i] = fy;
+    f[2 * (size_t)cap + i] = fz;
+}
+
+
+// ---- bank-aware row order.  ldg_patterns.cu shows that an LDG.256 warp gather is served one
+// QUAD of lanes (4 x 32 B = the 128-byte data path) per cycle when the four sectors sit at
+// four different positions of their 128-byte lines, whatever the lines are, and serialises on
+// equal positions.  With 32-byte records the position is j & 3.  Reorder every row so that at
+// step r lane q (= i & 3) reads a neighbour of class (r + q) & 3: a Latin square per quad, no
+// conflict while all four classes of all four lanes last; the tail (classes run out unevenly)
+// is filled with what is left.  The set of neighbours per row is unchanged.
+template <int NC>
+__global__ void __launch_bounds__( 128 )
+    k_reorder_rows( int *__restrict__ nb, const int *__restrict__ cnt, int stride, int n, int mode )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    const int c = cnt[i];
+    int cls[NC][128 / NC + 16];
+    int nc[NC], used[NC];
+    for ( int t = 0; t < NC; t++ )
+        nc[t] = used[t] = 0;
+    for ( int k = 0; k < c; k++ )
+    {
+        const int j = nb[TB( i, stride ) + k * 32];
+        const int b = j & ( NC - 1 );
+        if ( nc[b] < 128 / NC + 16 )
+            cls[b][nc[b]++] = j;
+    }
+    const int q = i & ( NC - 1 );
+    for ( int r = 0; r < c; r++ )
+    {
+        int b = ( r + q ) & ( NC - 1 );
+        if ( mode == 1 && used[b] >= nc[b] )
+        {
+            // class exhausted: take from the class with most entries left
+            int best = -1, left = 0;
+            for ( int t = 0; t < NC; t++ )
+                if ( nc[t] - used[t] > left )
+                {
+                    left = nc[t] - used[t];
+                    best = t;
+                }
+            b = best;
+        }
+        nb[TB( i, stride ) + r * 32] = cls[b][used[b]++];
+    }
 }
 
 // DP-only bound: same arithmetic, j data synthesised in registers (no gather)
@@ -219,11 +400,11 @@ __global__ void __launch_bounds__( 128 )
     const XT xi = ld_xt( xt + i );
     double fx = 0, fy = 0, fz = 0;
     const int c = cnt[i];
-    const int *p = nb + i;
+    const int *p = nb + TB( i, stride );
 #pragma unroll 4
     for ( int k = 0; k < c; k++ )
     {
-        const int j = __ldg( p + (size_t)k * stride );
+        const int j = __ldg( p + k * 32 );
         const double s = (double)( j & 7 ) * 0.25;
         const double dx = 0.5 + s, dy = 0.25 - s, dz = 1.0 + 0.5 * s;
         LJ_BODY( rcp3, lt_pos( rsq, cutsq ) )
@@ -243,10 +424,10 @@ __global__ void __launch_bounds__( 128 )
         return;
     int acc = 0;
     const int c = cnt[i];
-    const int *p = nb + i;
+    const int *p = nb + TB( i, stride );
 #pragma unroll 8
     for ( int k = 0; k < c; k++ )
-        acc += __ldg( p + (size_t)k * stride );
+        acc += __ldg( p + k * 32 );
     f[i] = (double)acc;
 }
 
@@ -294,11 +475,11 @@ __global__ void __launch_bounds__( 256 )
         const double xi = x[i], yi = y[i], zi = z[i];
         double fx = 0, fy = 0, fz = 0;
         const int c = cnt[i];
-        const int *p = nb + i;
+        const int *p = nb + TB( i, stride );
 #pragma unroll 4
         for ( int k = 0; k < c; k++ )
         {
-            const int j = __ldg( p + (size_t)k * stride ) & ( S - 1 );
+            const int j = __ldg( p + k * 32 ) & ( S - 1 );
             double xj, yj, zj;
             if ( MODE == 0 )
             {
@@ -361,7 +542,7 @@ __global__ void k_build( const XT *__restrict__ xt, int n, const int *__restrict
                 if ( j != i && dx * dx + dy * dy + dz * dz <= rsq )
                 {
                     if ( count < rows )
-                        nb[(size_t)count * stride + i] = j;
+                        nb[TB( i, stride ) + count * 32] = j;
                     count++;
                 }
             }
@@ -482,7 +663,7 @@ int main( int argc, char **argv )
     XT *d_xt;
     double *d_soa, *d_x3, *d_f, *d_f0;
     int *d_cs, *d_ca, *d_nb, *d_cnt;
-    const int stride = ( n + 31 ) & ~31, rows = 128;
+    const int rows = 128, stride = rows, natoms32 = ( n + 31 ) & ~31;
     CK( cudaMalloc( &d_xt, (size_t)cap * sizeof( XT ) ) );
     CK( cudaMalloc( &d_soa, 3 * (size_t)cap * 8 ) );
     CK( cudaMalloc( &d_x3, 3 * (size_t)cap * 8 ) );
@@ -490,7 +671,7 @@ int main( int argc, char **argv )
     CK( cudaMalloc( &d_f0, 3 * (size_t)cap * 8 ) );
     CK( cudaMalloc( &d_cs, ( ncells + 1 ) * 4 ) );
     CK( cudaMalloc( &d_ca, (size_t)ntot * 4 ) );
-    CK( cudaMalloc( &d_nb, (size_t)rows * stride * 4 ) );
+    CK( cudaMalloc( &d_nb, (size_t)rows * natoms32 * 4 ) );
     CK( cudaMalloc( &d_cnt, (size_t)cap * 4 ) );
     CK( cudaMemcpy( d_xt, hxt.data(), (size_t)cap * sizeof( XT ), cudaMemcpyHostToDevice ) );
     CK( cudaMemcpy( d_soa, hsoa.data(), 3 * (size_t)cap * 8, cudaMemcpyHostToDevice ) );
@@ -560,9 +741,115 @@ int main( int argc, char **argv )
     run( "v1 SoA 3xLDG.64 u2", [&] { k_v1<2><<<grid, 128>>>( x_, y_, z_, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
     run( "v2 AoS32 LDG.128+LDG.64", [&] { k_v2<<<grid, 128>>>( d_xt, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
     run( "v3 AoS24 3xLDG.64", [&] { k_v3<<<grid, 128>>>( d_x3, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
+    {
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = d_xt;
+        rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+        rd.res.linear.sizeInBytes = (size_t)cap * sizeof( XT );
+        cudaTextureDesc td = {};
+        td.readMode = cudaReadModeElementType;
+        cudaTextureObject_t tex = 0;
+        CK( cudaCreateTextureObject( &tex, &rd, &td, nullptr ) );
+        run( "tex: all via 2x tex1Dfetch", [&] { k_tex<0><<<grid, 128>>>( d_xt, tex, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
+        run( "tex: 1/2 TEX + 1/2 LDG.256", [&] { k_tex<1><<<grid, 128>>>( d_xt, tex, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
+        cudaResourceDesc rd2 = rd;
+        rd2.res.linear.desc = cudaCreateChannelDesc<int2>();
+        cudaTextureObject_t tex2 = 0;
+        CK( cudaCreateTextureObject( &tex2, &rd2, &td, nullptr ) );
+        cudaResourceDesc rdz = rd;
+        rdz.res.linear.devPtr = z_;
+        rdz.res.linear.desc = cudaCreateChannelDesc<int2>();
+        rdz.res.linear.sizeInBytes = (size_t)cap * 8;
+        cudaTextureObject_t texz = 0;
+        CK( cudaCreateTextureObject( &texz, &rdz, &td, nullptr ) );
+        std::vector<double2> hxy( cap );
+        for ( int i = 0; i < ntot; i++ )
+            hxy[i] = make_double2( x[3 * (size_t)i], x[3 * (size_t)i + 1] );
+        double2 *d_xy;
+        CK( cudaMalloc( &d_xy, (size_t)cap * 16 ) );
+        CK( cudaMemcpy( d_xy, hxy.data(), (size_t)cap * 16, cudaMemcpyHostToDevice ) );
+#define RUN_TEX2( NAME, F, A, B, U )                                                              \
+    run( NAME, [&] { k_tex2<F, A, B, U><<<grid, 128>>>( d_xt, tex, tex2, z_, texz, d_xy, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true )
+        {
+            cudaResourceDesc rdxy = rd;
+            rdxy.res.linear.devPtr = d_xy;
+            rdxy.res.linear.desc = cudaCreateChannelDesc<int4>();
+            rdxy.res.linear.sizeInBytes = (size_t)cap * 16;
+            cudaTextureObject_t texxy = 0;
+            CK( cudaCreateTextureObject( &texxy, &rdxy, &td, nullptr ) );
+#define RUN_TEX3( NAME, F, A, B, U )                                                              \
+    run( NAME, [&] { k_tex2<F, A, B, U><<<grid, 128>>>( d_xt, tex, texxy, z_, texz, d_xy, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true )
+            RUN_TEX3( "tex3 xy-texP+z-ldg64 all u4", 5, 1, 1, 4 );
+            RUN_TEX3( "tex3 xy-texP+z-ldg64 all u8", 5, 1, 1, 8 );
+            RUN_TEX3( "tex3 alternate roles u4", 6, 1, 1, 4 );
+            RUN_TEX3( "tex3 alternate roles u8", 6, 1, 1, 8 );
+            RUN_TEX3( "tex3 xy-texP+z-ldg64 3/4 u4", 5, 3, 4, 4 );
+        }
+        RUN_TEX2( "tex2 xy-ldg128+z-tex all u8", 3, 1, 1, 8 );
+        RUN_TEX2( "tex2 xy-ldg128+z-tex all u4 rcp3", 3, 1, 1, 16 + 4 );
+        RUN_TEX2( "tex2 xy-ldg128+z-tex all u8 rcp3", 3, 1, 1, 16 + 8 );
+        RUN_TEX2( "tex2 xy-ldg128+z-tex all u6", 3, 1, 1, 6 );
+        RUN_TEX2( "tex2 xy-ldg128+z-tex all u2", 3, 1, 1, 2 );
+        RUN_TEX2( "tex2 xy-ldg128+z-tex 7/8 u8", 3, 7, 8, 8 );
+        RUN_TEX2( "tex2 int4x2  1/2 u4", 0, 1, 2, 4 );
+        RUN_TEX2( "tex2 int4x2  1/2 u8", 0, 1, 2, 8 );
+        RUN_TEX2( "tex2 int4x2  3/8 u8", 0, 3, 8, 8 );
+        RUN_TEX2( "tex2 int4x2  5/8 u8", 0, 5, 8, 8 );
+        RUN_TEX2( "tex2 xy-tex+z-ldg64 all u4", 2, 1, 1, 4 );
+        RUN_TEX2( "tex2 xy-tex+z-ldg64 3/4 u4", 2, 3, 4, 4 );
+        RUN_TEX2( "tex2 xy-tex+z-ldg64 3/4 u8", 2, 3, 4, 8 );
+        RUN_TEX2( "tex2 xy-tex+z-ldg64 7/8 u8", 2, 7, 8, 8 );
+        RUN_TEX2( "tex2 xy-tex+z-ldg64 5/8 u8", 2, 5, 8, 8 );
+        RUN_TEX2( "tex2 xy-tex+z-ldg64 1/2 u4", 2, 1, 2, 4 );
+        RUN_TEX2( "tex2 xy-ldg128+z-tex all u4", 3, 1, 1, 4 );
+        RUN_TEX2( "tex2 xy-ldg128+z-tex 3/4 u4", 3, 3, 4, 4 );
+        RUN_TEX2( "tex2 xy-ldg128+z-tex 1/2 u4", 3, 1, 2, 4 );
+        RUN_TEX2( "tex2 xy-tex+z-tex all u4", 4, 1, 1, 4 );
+        RUN_TEX2( "tex2 xy-tex+z-tex 1/2 u4", 4, 1, 2, 4 );
+        RUN_TEX2( "tex2 xy-tex+z-tex 3/4 u4", 4, 3, 4, 4 );
+        run( "tex: 1/4 TEX + 3/4 LDG.256", [&] { k_tex<2><<<grid, 128>>>( d_xt, tex, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
+    }
     run( "dp-only (no gather)", [&] { k_dp_only<<<grid, 128>>>( d_xt, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, false );
     run( "index-stream only", [&] { k_idx_only<<<grid, 128>>>( d_nb, d_cnt, stride, n, d_f, cap ); }, false );
 
+    {
+        // bank-aware row orders (must come last: they permute the table in place)
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = z_;
+        rd.res.linear.desc = cudaCreateChannelDesc<int2>();
+        rd.res.linear.sizeInBytes = (size_t)cap * 8;
+        cudaTextureDesc td = {};
+        td.readMode = cudaReadModeElementType;
+        cudaTextureObject_t texz = 0;
+        CK( cudaCreateTextureObject( &texz, &rd, &td, nullptr ) );
+        std::vector<double2> hxy( cap );
+        for ( int i = 0; i < ntot; i++ )
+            hxy[i] = make_double2( x[3 * (size_t)i], x[3 * (size_t)i + 1] );
+        double2 *d_xy;
+        CK( cudaMalloc( &d_xy, (size_t)cap * 16 ) );
+        CK( cudaMemcpy( d_xy, hxy.data(), (size_t)cap * 16, cudaMemcpyHostToDevice ) );
+        auto both = [&]( const char *tag )
+        {
+            char name[96];
+            snprintf( name, sizeof name, "v0 LDG.256, rows %s", tag );
+            run( name, [&] { k_v0<<<grid, 128>>>( d_xt, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
+            snprintf( name, sizeof name, "xy-ldg128+z-tex u4, rows %s", tag );
+            run( name, [&] { k_tex2<3, 1, 1, 4><<<grid, 128>>>( d_xt, 0, 0, z_, texz, d_xy, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
+            snprintf( name, sizeof name, "xy-ldg128+z-tex u8, rows %s", tag );
+            run( name, [&] { k_tex2<3, 1, 1, 8><<<grid, 128>>>( d_xt, 0, 0, z_, texz, d_xy, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
+        };
+        k_reorder_rows<8><<<grid, 128>>>( d_nb, d_cnt, stride, n, 1 );
+        CK( cudaDeviceSynchronize() );
+        both( "8-class" );
+        k_reorder_rows<4><<<grid, 128>>>( d_nb, d_cnt, stride, n, 1 );
+        CK( cudaDeviceSynchronize() );
+        both( "4-class" );
+        k_reorder_rows<2><<<grid, 128>>>( d_nb, d_cnt, stride, n, 1 );
+        CK( cudaDeviceSynchronize() );
+        both( "2-class" );
+    }
     {
         constexpr int S = 4096, B = 4;
         const int g2 = ( n + B * 256 - 1 ) / ( B * 256 );

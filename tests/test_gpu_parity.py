@@ -141,12 +141,17 @@ def test_binning_matches_oracle(cb):
     assert np.array_equal(a["id"], d["id"][:n][perm])
 
 
-@pytest.mark.parametrize("group", [8, 1])
+# (nb_group, gather): default = one lane per atom with the texture-assisted split gather;
+# the 32-byte-record LDG.256 gather; 8 lanes per atom over the quad-grouped table
+SWEEPS = [(1, 1), (1, 0), (8, 0)]
+
+
+@pytest.mark.parametrize("group,gather", SWEEPS)
 @pytest.mark.parametrize("half", [False, True])
-def test_force_energy_on_oracle_state(cb, half, group):
+def test_force_energy_on_oracle_state(cb, half, group, gather):
     """Same atoms (owned + ghosts from the oracle's 6-phase build): neighbour sets
-    bit-exact, forces <= 1e-10 relative, energy to round-off.  Both table layouts /
-    sweep shapes: one lane per atom (default) and 8 lanes per atom."""
+    bit-exact, forces <= 1e-10 relative, energy to round-off, for every sweep shape /
+    gather path of the force kernel."""
     s = melted_state((10, 10, 10), 60, half)
     d = s.get()
     n, ng = d["n_local"], d["n_ghost"]
@@ -159,6 +164,7 @@ def test_force_energy_on_oracle_state(cb, half, group):
     ctx.set_atoms(d["x"][:n], d["v"][:n], None, d["type"][:n], d["id"][:n])
     ctx.append_ghosts(d["x"][n:], d["type"][n:], d["id"][n:])
     ctx.set_option("nb_group", group)
+    ctx.set_option("gather", gather)
     ctx.neigh_build(2.8, half, 0, 50)
     counts, rows = gpu_rows(ctx)
     ocounts, ooff, oneigh = s.list()
@@ -184,6 +190,12 @@ def test_force_energy_on_oracle_state(cb, half, group):
     ctx.force(half)
     b = ctx.get_atoms()
     assert np.abs(b["f"] - 2 * a["f"]).max() <= 1e-12 * scale
+    if not half and group == 1:
+        # the two gather paths run the same arithmetic in the same order: identical bits
+        ctx.set_option("gather", 1 - gather)
+        ctx.zero_force()
+        ctx.force(half)
+        assert np.array_equal(ctx.get_atoms()["f"], a["f"])
 
 
 @pytest.mark.parametrize("group", [8, 1])
