@@ -388,6 +388,39 @@ __global__ void __launch_bounds__( 128 )
     }
 }
 
+
+// the product's texture-assisted kernel shape with occupancy / unroll knobs
+template <int U, int MINB, int BS>
+__global__ void __launch_bounds__( BS, ( MINB % 100 ) )
+    k_split( const XT *__restrict__ xt, const double2 *__restrict__ xy, cudaTextureObject_t texz,
+             const int *__restrict__ nb, const int *__restrict__ cnt, int stride, int n,
+             double *__restrict__ f, int cap, double lj1, double lj2, double cutsq )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( i >= n )
+        return;
+    const XT xi = ld_xt( xt + i );
+    double fx = 0, fy = 0, fz = 0;
+    const int c = cnt[i];
+    const int *p = nb + TB( i, stride );
+#pragma unroll( U )
+    for ( int k = 0; k < c; k++ )
+    {
+        const int j = __ldg( p + k * 32 );
+        double2 t;
+        if ( MINB >= 100 )
+            asm volatile( "ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"( t.x ), "=d"( t.y ) : "l"( xy + j ) );
+        else
+            t = __ldg( xy + j );
+        const int2 d = tex1Dfetch<int2>( texz, j );
+        const double dx = xi.x - t.x, dy = xi.y - t.y, dz = xi.z - __hiloint2double( d.y, d.x );
+        LJ_BODY( rcp5, rsq < cutsq )
+    }
+    f[i] = fx;
+    f[(size_t)cap + i] = fy;
+    f[2 * (size_t)cap + i] = fz;
+}
+
 // DP-only bound: same arithmetic, j data synthesised in registers (no gather)
 __global__ void __launch_bounds__( 128 )
     k_dp_only( const XT *__restrict__ xt, const int *__restrict__ nb, const int *__restrict__ cnt,
@@ -840,6 +873,19 @@ int main( int argc, char **argv )
             snprintf( name, sizeof name, "xy-ldg128+z-tex u8, rows %s", tag );
             run( name, [&] { k_tex2<3, 1, 1, 8><<<grid, 128>>>( d_xt, 0, 0, z_, texz, d_xy, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
         };
+#define RUN_SPLIT( U, MINB, BS )                                                                  \
+    run( "split U" #U " minb" #MINB " bs" #BS, [&] { k_split<U, MINB, BS><<<( n + BS - 1 ) / BS, BS>>>( d_xt, d_xy, texz, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true )
+        RUN_SPLIT( 4, 1, 128 );
+        RUN_SPLIT( 6, 1, 128 );
+        RUN_SPLIT( 4, 10, 128 );
+        RUN_SPLIT( 6, 10, 128 );
+        RUN_SPLIT( 4, 12, 128 );
+        RUN_SPLIT( 6, 12, 128 );
+        RUN_SPLIT( 8, 12, 128 );
+        RUN_SPLIT( 4, 101, 128 );
+        RUN_SPLIT( 6, 101, 128 );
+        RUN_SPLIT( 6, 5, 256 );
+        RUN_SPLIT( 6, 20, 64 );
         k_reorder_rows<8><<<grid, 128>>>( d_nb, d_cnt, stride, n, 1 );
         CK( cudaDeviceSynchronize() );
         both( "8-class" );
