@@ -284,7 +284,22 @@ __global__ void __launch_bounds__( 128 )
         double xj, yj, zj;
         if ( ( k % TEX_DEN ) < TEX_NUM )
         {
-            if ( FETCH == 5 || ( FETCH == 6 && ( k & 1 ) ) )
+            if ( FETCH == 7 )
+            { // x through LDG.64 (SoA), y and z through two 8-byte TEX fetches
+                const int2 b = tex1Dfetch<int2>( tex4, j ); // tex4 is bound to the SoA y array in this mode
+                const int2 d = tex1Dfetch<int2>( texz, j );
+                xj = __ldg( zs - 2 * (size_t)cap + j ); // d_soa holds x | y | z back to back
+                yj = __hiloint2double( b.y, b.x );
+                zj = __hiloint2double( d.y, d.x );
+            }
+            else if ( FETCH == 8 )
+            { // no TEX at all: x,y through LDG.128 (packed), z through LDG.64 (SoA)
+                const double2 t = __ldg( xy + j );
+                xj = t.x;
+                yj = t.y;
+                zj = __ldg( zs + j );
+            }
+            else if ( FETCH == 5 || ( FETCH == 6 && ( k & 1 ) ) )
             { // x,y through TEX from the PACKED xy array (texel j), z through LDG.64
                 const int4 a = tex1Dfetch<int4>( tex2, j ); // tex2 is bound to xy as int4 in this mode
                 xj = __hiloint2double( a.y, a.x );
@@ -819,6 +834,16 @@ int main( int argc, char **argv )
             RUN_TEX3( "tex3 alternate roles u8", 6, 1, 1, 8 );
             RUN_TEX3( "tex3 xy-texP+z-ldg64 3/4 u4", 5, 3, 4, 4 );
         }
+        {
+            cudaResourceDesc rdy = rdz;
+            rdy.res.linear.devPtr = y_;
+            cudaTextureObject_t texy = 0;
+            CK( cudaCreateTextureObject( &texy, &rdy, &td, nullptr ) );
+            run( "x-ldg64 + y-tex8 + z-tex8 u6", [&] { k_tex2<7, 1, 1, 6><<<grid, 128>>>( d_xt, texy, tex2, z_, texz, d_xy, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
+            run( "x-ldg64 + y-tex8 + z-tex8 u4", [&] { k_tex2<7, 1, 1, 4><<<grid, 128>>>( d_xt, texy, tex2, z_, texz, d_xy, d_nb, d_cnt, stride, n, d_f, cap, lj1, lj2, cutsq ); }, true );
+        }
+        RUN_TEX2( "no TEX: xy-ldg128 + z-ldg64 u6", 8, 1, 1, 6 );
+        RUN_TEX2( "no TEX: xy-ldg128 + z-ldg64 u4", 8, 1, 1, 4 );
         RUN_TEX2( "tex2 xy-ldg128+z-tex all u8", 3, 1, 1, 8 );
         RUN_TEX2( "tex2 xy-ldg128+z-tex all u4 rcp3", 3, 1, 1, 16 + 4 );
         RUN_TEX2( "tex2 xy-ldg128+z-tex all u8 rcp3", 3, 1, 1, 16 + 8 );
