@@ -50,11 +50,11 @@ __device__ __forceinline__ bool half_valid( const XT &a, const XT &b )
 // ---------------------------------------------------------------------------
 // K staged candidates against this lane's atom: FP32 decisions, ONE warp vote for the
 // (rare) exact FP64 re-evaluation, then in-order, branch-free appends to the lane's row.
-template <bool HALF, int K>
+template <bool HALF, int K, bool GROUPED>
 __device__ __forceinline__ void
 sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const XT &xi, float xr,
              float yr, float zr, int i, float r2lo, float r2hi, float tolx, double rsqr,
-             char *row0, int nb_rows, int grouped, int &count )
+             char *row0, int nb_rows, int &count )
 {
     // i < 0 marks an inactive lane: its r2lo/r2hi are -1 so nothing is ever accepted
     float4 c[K];
@@ -99,7 +99,7 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
         // predicated store (no branch).  Tiled layout: entry n of this lane's column is 128
         // bytes further on; grouped layout: 8 consecutive entries per 128-byte chunk line
         const int st = ( ok[k] && count < nb_rows ) ? 1 : 0;
-        const unsigned off = grouped ? ( ( (unsigned)count >> 3 ) << 7 ) + ( ( (unsigned)count & 7u ) << 2 )
+        const unsigned off = GROUPED ? ( ( (unsigned)count >> 3 ) << 7 ) + ( ( (unsigned)count & 7u ) << 2 )
                                      : (unsigned)count << 7;
         char *dst = row0 + (unsigned long long)off;
         asm volatile( "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b32 [%0], %1;\n\t}"
@@ -114,12 +114,12 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
 #define NB_THREADS ( 32 * NBC )
 #define NB_STAGE 1280 // candidates per staging chunk (20 KB)
 
-template <bool HALF>
+template <bool HALF, bool GROUPED>
 __global__ void __launch_bounds__( NB_THREADS )
     k_neigh_build( const XT *__restrict__ xt, int n_local, GridDesc g,
                    const int *__restrict__ cell_start, const int *__restrict__ cell_atoms,
                    double rsqr, double3 centre, int *__restrict__ nb, int nb_stride, int nb_rows,
-                   int nb_group, int *__restrict__ nb_count, int *__restrict__ d_max )
+                   int *__restrict__ nb_count, int *__restrict__ d_max )
 {
     __shared__ float4 cand[NB_STAGE];
     __shared__ int run_src[9], run_off[10];
@@ -228,8 +228,7 @@ __global__ void __launch_bounds__( NB_THREADS )
             xi = ld_xt( xt + i );
         const float xr = active ? (float)( xi.x - ox ) : 0.f, yr = active ? (float)( xi.y - oy ) : 0.f,
                     zr = active ? (float)( xi.z - oz ) : 0.f;
-        const int grouped = nb_group == 8;
-        char *const row0 = (char *)( nb + nb_entry( nb_group, active ? i : 0, 0, nb_rows ) );
+        char *const row0 = (char *)( nb + nb_entry( GROUPED ? 8 : 1, active ? i : 0, 0, nb_rows ) );
         int count = 0;
 
         for ( int chunk = 0; chunk < total; chunk += NB_STAGE )
@@ -286,11 +285,11 @@ __global__ void __launch_bounds__( NB_THREADS )
                 const int n4 = ( e - b ) >> 2;
                 const float4 *cp = cand + b;
                 for ( int q = 0; q < n4; q++, cp += 4 )
-                    sweep_group<HALF, 4>( cp, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx, rsqr, row0,
-                                          nb_rows, grouped, count );
+                    sweep_group<HALF, 4, GROUPED>( cp, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx, rsqr,
+                                                   row0, nb_rows, count );
                 for ( int t = b + 4 * n4; t < e; t++ )
-                    sweep_group<HALF, 1>( cand + t, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx, rsqr,
-                                          row0, nb_rows, grouped, count );
+                    sweep_group<HALF, 1, GROUPED>( cand + t, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx,
+                                                   rsqr, row0, nb_rows, count );
             }
         }
         if ( active )
@@ -466,14 +465,20 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
         if ( n_local > 0 )
         {
             const int blocks = g.n[0] * g.n[1] * ( ( g.n[2] + NBC - 1 ) / NBC );
-            if ( half )
-                k_neigh_build<true><<<blocks, NB_THREADS, 0, s>>>(
-                    ctx->xt, n_local, g, ctx->cell_start, ctx->cell_atoms, rsqr, centre, ctx->nb,
-                    stride, rows, ctx->nb_group, ctx->nb_count, d_max );
+#define NB_LAUNCH( H, G )                                                                         \
+    k_neigh_build<H, G><<<blocks, NB_THREADS, 0, s>>>( ctx->xt, n_local, g, ctx->cell_start,      \
+                                                       ctx->cell_atoms, rsqr, centre, ctx->nb,    \
+                                                       stride, rows, ctx->nb_count, d_max )
+            const bool grouped = ctx->nb_group == 8;
+            if ( half && grouped )
+                NB_LAUNCH( true, true );
+            else if ( half )
+                NB_LAUNCH( true, false );
+            else if ( grouped )
+                NB_LAUNCH( false, true );
             else
-                k_neigh_build<false><<<blocks, NB_THREADS, 0, s>>>(
-                    ctx->xt, n_local, g, ctx->cell_start, ctx->cell_atoms, rsqr, centre, ctx->nb,
-                    stride, rows, ctx->nb_group, ctx->nb_count, d_max );
+                NB_LAUNCH( false, false );
+#undef NB_LAUNCH
             CBMD_LAUNCH_CHECK( ctx );
         }
         // NeighborList<>::maxNeighbor (neighbor_verlet.h:58-59)

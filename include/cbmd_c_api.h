@@ -167,7 +167,13 @@ extern "C"
     /* synchronises, then returns accumulated milliseconds and region count */
     int cbmd_timing_get( cbmd_ctx *ctx, int bucket, double *ms, int64_t *count );
     int cbmd_timing_reset( cbmd_ctx *ctx );
-    /* kernel variant switches for A/B measurements, e.g. "force_variant"=0|1 */
+    /* kernel variant switches (results are identical to round-off; for A/B measurements):
+     *   "gather"   1 (default) single-type full-list force gathers x,y by LDG.128 from a packed
+     *              mirror and z through the texture path; 0 = 32-byte records by LDG.256
+     *   "nb_group" 1 (default) one lane per atom over the 32-atom tiled table; 8 = eight lanes
+     *              per atom over a quad-grouped table (takes effect at the next cbmd_neigh_build)
+     *   "overlap"  1 (default) halo refresh on a second stream under the interior force tiles
+     * Environment overrides read at cbmd_create: CBMD_GATHER, CBMD_NB_GROUP, CBMD_OVERLAP. */
     int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value );
 
 #ifdef __cplusplus
