@@ -524,3 +524,59 @@ def test_long_cutoff_variant_matches_oracle(cb):
     fa = a["f"][: a["n_local"]][np.argsort(a["id"][: a["n_local"]])]
     fb = b["f"][: b["n_local"]][np.argsort(b["id"][: b["n_local"]])]
     assert np.abs(fa - fb).max() <= 1e-9 * np.abs(fb).max()
+
+
+def test_position_mirror_follows_every_way_atoms_move(cb):
+    """The texture-assisted force kernel reads a split copy of the positions that the
+    integrator and the halo refresh maintain; every other path (re-upload with a larger
+    capacity, migration, cell sort, ghost rebuild, switching the option off and on) must
+    leave it detectably stale.  After each such sequence the forces have to be bit-identical
+    to the record-gather kernel's (same arithmetic, same order)."""
+    from cabanamd_b200.harness import Simulation
+
+    def forces(sim, gather):
+        sim.ctx.set_option("gather", gather)
+        sim.ctx.zero_force()
+        sim.ctx.force(False)
+        a = sim.ctx.get_atoms()
+        return a["f"][: a["n_local"]].copy()
+
+    def check(sim, what):
+        f_tex = forces(sim, 1)
+        f_rec = forces(sim, 0)
+        assert np.array_equal(f_tex, f_rec), what
+        sim.ctx.set_option("gather", 1)
+
+    small = melted_state((6, 6, 6), 30)
+    d, dom = small.get(), small.domain()
+    n = d["n_local"]
+    sim = Simulation(device=0)
+    sim.set_box(dom["llo"], dom["lhi"])
+    sim.set_atoms(d["x"][:n], d["v"][:n], d["type"][:n], d["id"][:n])
+    sim.setup()
+    check(sim, "after setup")
+    sim.run(7, 0)                       # integrator + halo refresh keep the mirror current
+    check(sim, "after 7 steps")
+    sim.ctx.set_option("gather", 0)     # mirror not maintained while the option is off
+    sim.run(5, 0)
+    check(sim, "after 5 steps with the option off")
+    sim.run(25, 0)                      # crosses a rebuild: migration, sort, ghost rebuild
+    check(sim, "after a rebuild step")
+    # a larger system through the same context: capacity grows, mirror + texture are re-made
+    big = melted_state((9, 9, 9), 20)
+    d, dom = big.get(), big.domain()
+    n = d["n_local"]
+    sim.set_box(dom["llo"], dom["lhi"])
+    sim.set_atoms(d["x"][:n], d["v"][:n], d["type"][:n], d["id"][:n])
+    sim.setup()
+    check(sim, "after re-upload with a larger capacity")
+    sim.run(21, 0)
+    check(sim, "after 21 more steps")
+    # and the trajectory itself still matches the oracle
+    big.run(21)
+    a, b = sim.ctx.get_atoms(), big.get()
+    xa = a["x"][: a["n_local"]][np.argsort(a["id"][: a["n_local"]])]
+    xb = b["x"][: b["n_local"]][np.argsort(b["id"][: b["n_local"]])]
+    L = np.array(dom["lhi"]) - np.array(dom["llo"])
+    dx = (xa - xb + L / 2) % L - L / 2
+    assert np.abs(dx).max() < 1e-9
