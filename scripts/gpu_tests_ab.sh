@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-1 (session 4) GPU check: parity tests incl. the grouped (8 lanes/atom) sweeps and the
+# parity tests incl. the grouped (8 lanes/atom) sweeps and the
 # new file-format paths, then the A/B bench of the two sweep shapes.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
