@@ -614,42 +614,53 @@ extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
         CBMD_CUDA( cudaEventRecord( ctx->ev_x, ctx->stream ) );
         CBMD_CUDA( cudaStreamWaitEvent( s, ctx->ev_x, 0 ) );
     }
-    for ( int ph = 0; ph < 6; ph++ )
+    // The two phases of one dimension are independent of each other: the odd phase never
+    // sends what the even phase has just received (cbmd_exchange_halo, comm_mpi_impl.h:301-303).
+    // They therefore share ONE NCCL group (one launch, both directions in flight together);
+    // the dimensions stay ordered because y forwards x ghosts and z forwards x and y ghosts.
+    for ( int d = 0; d < 3; d++ )
     {
-        HaloPhase &P = ctx->phase[ph];
-        const int d = ph / 2;
-        if ( P.peer_send == ctx->rank )
+        HaloPhase *pair[2] = { &ctx->phase[2 * d], &ctx->phase[2 * d + 1] };
+        if ( pair[0]->peer_send == ctx->rank )
         {
-            if ( P.n_recv > 0 )
-            {
-                k_halo_update_self<<<div_up( P.n_recv, 256 ), 256, 0, s>>>(
-                    ctx->xt, P.send_idx, P.n_recv, P.recv_first, d, P.shift );
-                CBMD_LAUNCH_CHECK( ctx );
-            }
+            for ( HaloPhase *P : pair )
+                if ( P->n_recv > 0 )
+                {
+                    k_halo_update_self<<<div_up( P->n_recv, 256 ), 256, 0, s>>>(
+                        ctx->xt, P->send_idx, P->n_recv, P->recv_first, d, P->shift );
+                    CBMD_LAUNCH_CHECK( ctx );
+                }
             continue;
         }
-        ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, (size_t)( P.n_send + 1 ) * sizeof( XT ), s );
-        XT *sx = (XT *)ctx->sendbuf;
-        if ( P.n_send > 0 )
-        {
-            k_halo_pack<<<div_up( P.n_send, 256 ), 256, 0, s>>>( ctx->xt, ctx->id, P.send_idx,
-                                                                 P.n_send, sx, nullptr );
-            CBMD_LAUNCH_CHECK( ctx );
-        }
+        ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes,
+                    (size_t)( pair[0]->n_send + pair[1]->n_send + 2 ) * sizeof( XT ), s );
+        XT *sx[2] = { (XT *)ctx->sendbuf, (XT *)ctx->sendbuf + pair[0]->n_send + 1 };
+        for ( int k = 0; k < 2; k++ )
+            if ( pair[k]->n_send > 0 )
+            {
+                k_halo_pack<<<div_up( pair[k]->n_send, 256 ), 256, 0, s>>>(
+                    ctx->xt, ctx->id, pair[k]->send_idx, pair[k]->n_send, sx[k], nullptr );
+                CBMD_LAUNCH_CHECK( ctx );
+            }
+        // with two ranks in this dimension both phases talk to the same peer: sends and
+        // receives are issued in phase order on both sides, which is how NCCL pairs them
         CBMD_NCCL( ncclGroupStart() );
-        if ( P.n_send > 0 )
-            CBMD_NCCL( ncclSend( sx, (size_t)P.n_send * sizeof( XT ), ncclChar, P.peer_send,
-                                 ctx->nccl, s ) );
-        if ( P.n_recv > 0 )
-            CBMD_NCCL( ncclRecv( ctx->xt + P.recv_first, (size_t)P.n_recv * sizeof( XT ), ncclChar,
-                                 P.peer_recv, ctx->nccl, s ) );
+        for ( int k = 0; k < 2; k++ )
+            if ( pair[k]->n_send > 0 )
+                CBMD_NCCL( ncclSend( sx[k], (size_t)pair[k]->n_send * sizeof( XT ), ncclChar,
+                                     pair[k]->peer_send, ctx->nccl, s ) );
+        for ( int k = 0; k < 2; k++ )
+            if ( pair[k]->n_recv > 0 )
+                CBMD_NCCL( ncclRecv( ctx->xt + pair[k]->recv_first, (size_t)pair[k]->n_recv * sizeof( XT ),
+                                     ncclChar, pair[k]->peer_recv, ctx->nccl, s ) );
         CBMD_NCCL( ncclGroupEnd() );
-        if ( P.n_recv > 0 && P.shift != 0.0 )
-        {
-            k_halo_shift<<<div_up( P.n_recv, 256 ), 256, 0, s>>>( ctx->xt, P.recv_first, P.n_recv,
-                                                                  d, P.shift );
-            CBMD_LAUNCH_CHECK( ctx );
-        }
+        for ( HaloPhase *P : pair )
+            if ( P->n_recv > 0 && P->shift != 0.0 )
+            {
+                k_halo_shift<<<div_up( P->n_recv, 256 ), 256, 0, s>>>( ctx->xt, P->recv_first, P->n_recv, d,
+                                                                       P->shift );
+                CBMD_LAUNCH_CHECK( ctx );
+            }
     }
     if ( ov )
     {
