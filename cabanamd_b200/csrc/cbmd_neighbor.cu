@@ -543,6 +543,16 @@ extern "C" int cbmd_neigh_get( cbmd_ctx *ctx, int *counts, int64_t *offsets, int
     CBMD_API_END
 }
 
+extern "C" int64_t cbmd_table_offset( int nb_group, int atom, int n, int row_capacity )
+{
+    return (int64_t)nb_entry( nb_group == 8 ? 8 : 1, atom, n, row_capacity );
+}
+
+extern "C" int64_t cbmd_table_size( int nb_group, int n_atoms, int row_capacity )
+{
+    return (int64_t)nb_table_size( nb_group == 8 ? 8 : 1, ( n_atoms + 31 ) & ~31, row_capacity );
+}
+
 extern "C" int cbmd_neigh_sizes( cbmd_ctx *ctx, int64_t *total, int *max_neigh )
 {
     CBMD_API_BEGIN

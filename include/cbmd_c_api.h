@@ -167,6 +167,12 @@ extern "C"
     /* synchronises, then returns accumulated milliseconds and region count */
     int cbmd_timing_get( cbmd_ctx *ctx, int bucket, double *ms, int64_t *count );
     int cbmd_timing_reset( cbmd_ctx *ctx );
+    /* Layout of the device Verlet table (host arithmetic only, no device needed): element
+     * offset of neighbour n of atom i for nb_group 1 (tiles of 32 atoms) or 8 (quads of atoms,
+     * 8 consecutive entries per 128-byte line), and the table size in elements for n_atoms
+     * rounded up to a multiple of 32.  Lets tests pin the addressing the kernels share. */
+    int64_t cbmd_table_offset( int nb_group, int atom, int n, int row_capacity );
+    int64_t cbmd_table_size( int nb_group, int n_atoms, int row_capacity );
     /* kernel variant switches (results are identical to round-off; for A/B measurements):
      *   "gather"   1 (default) single-type full-list force gathers x,y by LDG.128 from a packed
      *              mirror and z through the texture path; 0 = 32-byte records by LDG.256
