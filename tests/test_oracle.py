@@ -232,3 +232,36 @@ def test_dims_create():
                    (6, (3, 2, 1)), (12, (3, 2, 2))]:
         L.orc_dims_create(n, O.ip(g))
         assert tuple(g) == exp
+
+
+def test_pair_force_and_energy_closed_form():
+    """Pin the oracle's LJ arithmetic against the closed form the reference's tables encode
+    (force_lj_cabana_neigh_impl.h:62-89,178-195,294-302): for one pair at distance r,
+    F = (48 eps s^12 / r^13 - 24 eps s^6 / r^7) along the bond, E = 4 eps ((s/r)^12 - (s/r)^6)
+    minus the same expression at the cutoff, per-type-pair coefficients, strict r^2 < rc^2."""
+    eps = np.array([[1.0, 0.7], [0.7, 1.3]])
+    sig = np.array([[1.0, 1.1], [1.1, 0.9]])
+    cut = np.array([[2.5, 2.2], [2.2, 2.0]])
+    lj1 = 48.0 * eps * sig ** 12
+    lj2 = 24.0 * eps * sig ** 6
+    cutsq = cut * cut
+    rng = np.random.default_rng(11)
+    for ti, tj in ((0, 0), (0, 1), (1, 1)):
+        for r in (0.95, 1.12, 1.7, cut[ti, tj] - 1e-9, cut[ti, tj], cut[ti, tj] + 1e-9):
+            u = rng.normal(size=3)
+            u /= np.linalg.norm(u)
+            x = np.array([[1.0, 2.0, 3.0], [1.0, 2.0, 3.0] + r * u])
+            t = np.array([ti, tj], dtype=np.int32)
+            rsq = float(np.sum((x[0] - x[1]) ** 2))
+            inside = rsq < cutsq[ti, tj]
+            e, s = eps[ti, tj], sig[ti, tj]
+            fmag = 48 * e * s ** 12 / r ** 13 - 24 * e * s ** 6 / r ** 7 if inside else 0.0
+            lj = lambda d: 4 * e * ((s / d) ** 12 - (s / d) ** 6)
+            for half in (False, True):
+                nl = O.NeighList().brute(x, 2, 3.0, half)
+                f = nl.force(x, t, half, lj1, lj2, cutsq)
+                want = np.array([-fmag * u, fmag * u])       # repulsive => pushes atom 0 away from atom 1
+                assert np.abs(f - want).max() <= 1e-12 * max(1.0, abs(fmag))
+                pe = nl.energy(x, t, half, lj1, lj2, cutsq)
+                e_want = lj(r) - lj(cut[ti, tj]) if inside else 0.0
+                assert abs(pe - e_want) <= 1e-12 * max(1.0, abs(e_want))
