@@ -12,9 +12,14 @@
 //       d^2 <= rc^2, i != j, ghost rows empty)           unit_test/tstNeighbor.hpp:76-190
 //   (2) the reference's tstIntegrator reversibility check unit_test/tstIntegrator.hpp:83-137
 //   (3) physics known answers derived from the reference formulas (in.lj step 0:
-//       T=1.400000, PotE=-6.332812, ETot=-4.232820)
-// Force / energy / comm outputs have no golden vectors in the reference tree:
-// for those rows parity is "unpinned by the reference's tests" (SURVEY.md 8c).
+//       T=1.400000, PotE=-6.332812, ETot=-4.232820), closed-form pair force / energy
+//   (4) an external golden trajectory: the published LAMMPS bench/in.lj log (the deck
+//       input/in.lj derives from; the reference copies LAMMPS' per-atom velocity
+//       generator, inputFile.h:73-148).  With that deck's parameters this code prints
+//       the log's step-0 line (1.44 -6.7733681 -4.6134356) and its step-100 line
+//       (0.7574531 -5.7585055 -4.6223613) to all seven digits     tests/test_oracle.py
+// Force / energy / comm outputs have no golden vectors in the reference tree itself:
+// those rows are "unpinned by the reference's tests"  and rest on (3)-(4).
 //
 // Every function cites the reference file:line it follows (paths relative to
 // /root/reference/src unless stated).  [Cabana] marks semantics of the

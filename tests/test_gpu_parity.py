@@ -580,3 +580,23 @@ def test_position_mirror_follows_every_way_atoms_move(cb):
     L = np.array(dom["lhi"]) - np.array(dom["llo"])
     dx = (xa - xb + L / 2) % L - L / 2
     assert np.abs(dx).max() < 1e-9
+
+
+def test_lammps_bench_lj_step100_known_answer_gpu(cb):
+    """The CUDA path against the published LAMMPS `bench/in.lj` log, step 100:
+    Temp 0.7574531, E_pair -5.7585055, TotEng -4.6223613 (see tests/test_oracle.py)."""
+    from test_oracle import LAMMPS_BENCH_LJ_STEP100, unshifted_thermo
+    from cabanamd_b200.harness import Simulation
+
+    ref = O.Sim(mass=[1.0]).create_lattice_fcc(cells=(20, 20, 20), temp=1.44)
+    d, dom = ref.get(), ref.domain()
+    sim = Simulation(device=0, mass=(1.0,))
+    sim.set_box(dom["llo"], dom["lhi"])
+    sim.set_atoms(d["x"], d["v"], d["type"], d["id"])
+    sim.setup()
+    sim.run(100, 0)
+    n = sim.N
+    _, off, nb = sim.ctx.neigh_get()
+    x_all = sim.ctx.get_atoms(fields="x")["x"]
+    got = unshifted_thermo(x_all, off, nb, n, sim.temperature(), sim.potential() / n, sim.kinetic() / n)
+    assert got == LAMMPS_BENCH_LJ_STEP100

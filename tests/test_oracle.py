@@ -265,3 +265,48 @@ def test_pair_force_and_energy_closed_form():
                 pe = nl.energy(x, t, half, lj1, lj2, cutsq)
                 e_want = lj(r) - lj(cut[ti, tj]) if inside else 0.0
                 assert abs(pe - e_want) <= 1e-12 * max(1.0, abs(e_want))
+
+
+def test_lammps_bench_lj_step0_known_answer():
+    """External known answer: the step-0 thermo line of the LAMMPS `bench/in.lj` log (the deck
+    CabanaMD's input/in.lj is derived from; 32 000 atoms, fcc rho*=0.8442, lj/cut 2.5, mass 1,
+    T = 1.44):  `0  1.44  -6.7733681  0  -4.6134356  -5.0197073`.  LAMMPS does not shift the
+    pair energy; the reference does (force_lj_cabana_neigh_impl.h:294-302), by
+    4((1/2.5)^12 - (1/2.5)^6) for each of the 54 lattice neighbours inside the cutoff."""
+    s = O.Sim(mass=[1.0]).create_lattice_fcc(cells=(20, 20, 20), temp=1.44).setup()
+    n = s.natoms
+    assert n == 32000
+    shift = 4.0 * (2.5 ** -12 - 2.5 ** -6)
+    e_pair = s.potential() / n + 0.5 * 54 * shift        # undo the shift: 27 pairs per atom
+    assert f"{e_pair:.7f}" == "-6.7733681"
+    assert f"{s.temperature():.2f}" == "1.44"
+    assert f"{e_pair + s.kinetic() / n:.7f}" == "-4.6134356"
+
+
+LAMMPS_BENCH_LJ_STEP100 = ("0.7574531", "-5.7585055", "-4.6223613")  # Temp, E_pair, TotEng
+
+
+def unshifted_thermo(x_all, offsets, neigh, n, T, pe_shifted_per_atom, ke_per_atom):
+    """Temp, E_pair, TotEng as LAMMPS prints them: the reference's pair energy is shifted
+    to zero at the cutoff, LAMMPS' is not, so add the shift back for every pair inside 2.5."""
+    i = np.repeat(np.arange(len(offsets) - 1), np.diff(offsets))
+    r2 = ((x_all[i] - x_all[neigh]) ** 2).sum(axis=1)
+    pairs_per_atom = 0.5 * np.count_nonzero(r2 < 6.25) / n
+    e_pair = pe_shifted_per_atom + 4.0 * (2.5 ** -12 - 2.5 ** -6) * pairs_per_atom
+    return f"{T:.7f}", f"{e_pair:.7f}", f"{e_pair + ke_per_atom:.7f}"
+
+
+def test_lammps_bench_lj_step100_known_answer():
+    """External known answer for the WHOLE path: line `100  0.7574531  -5.7585055  0
+    -4.6223613  0.20726105` of the LAMMPS `bench/in.lj` log (32 000 atoms, velocity all create
+    1.44 87287 loop geom, neighbor 0.3 bin, neigh_modify every 20, 100 steps of fix nve at
+    dt 0.005).  Reproducing its seven printed digits needs the same lattice fill, the same
+    hashed per-atom velocity generator and momentum/temperature scaling (inputFile.h:73-148,
+    inputFile_impl.h:536-868), a neighbour list that misses no pair inside the cutoff between
+    rebuilds, the LJ force and velocity-Verlet arithmetic: every stage the oracle restates."""
+    s = O.Sim(mass=[1.0]).create_lattice_fcc(cells=(20, 20, 20), temp=1.44).setup()
+    s.run(100, 0)
+    n = s.natoms
+    _, off, nb = s.list()  # step 100 is a rebuild step: the list holds every pair inside 2.8
+    got = unshifted_thermo(s.get()["x"], off, nb, n, s.temperature(), s.potential() / n, s.kinetic() / n)
+    assert got == LAMMPS_BENCH_LJ_STEP100
