@@ -163,7 +163,6 @@ struct cbmd_ctx
     int *h_pinned_i = nullptr;
 
     // options
-    int force_variant = 0;
 
     // CUDA-event timers (cbmd_timing_*)
     bool timing = false;

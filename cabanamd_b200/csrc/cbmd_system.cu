@@ -317,9 +317,7 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
 {
     CBMD_API_BEGIN
     std::string n( name ? name : "" );
-    if ( n == "force_variant" )
-        ctx->force_variant = (int)value;
-    else if ( n == "overlap" )
+    if ( n == "overlap" )
         ctx->overlap = (int)value;
     else if ( n == "gather" )
     {
