@@ -3,9 +3,11 @@
 // instantiated over a plain host particle store, so the CPU test-suite can pin the
 // formats without a device.  Not part of the product path.
 //
-//   cbmd_io_tool data IN OUT [precision [atom_style [xlo xhi ylo yhi zlo zhi]]]
+//   cbmd_io_tool data IN OUT [precision [atom_style [xlo xhi ylo yhi zlo zhi [rank nranks]]]]
 //       parse IN as one rank (optionally owning only the given sub-box), write OUT with
-//       write_data, print `N N_local ntypes | masses`
+//       write_data, print `N N_local ntypes | masses`.  With rank/nranks the call plays ONE
+//       rank of a multi-rank write_data: ranks > 0 leave their part files, rank 0 (run last)
+//       assembles the file
 //   cbmd_io_tool vtk IN PATTERN STEP RANK NRANKS [WORKERS]
 //       parse IN, write the particle dump(s) through the background writer
 //   cbmd_io_tool dump IN PATH STEP RANK          binary dump of the parsed state (f = -x)
@@ -106,6 +108,11 @@ int main( int argc, char *argv[] )
             if ( !load( argv[2], s ) )
                 return 2;
             OneRank comm;
+            if ( argc > 13 )
+            {
+                comm.rank = std::atoi( argv[12] );
+                comm.size = std::atoi( argv[13] );
+            }
             write_data( &s, &comm, argv[3], precision );
             std::printf( "%d %d %d |", s.N, s.N_local, s.ntypes );
             for ( double m : s.mass )

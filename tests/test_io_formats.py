@@ -406,3 +406,27 @@ def test_dumpbinary_then_correctness(tmp_path):
     assert p.returncode == 0, p.stderr + err
     vals = np.array([[float(v) for v in ln.split()] for ln in (tmp_path / "corr_half.txt").read_text().splitlines()[1:]])
     assert vals.shape == (3, 7) and vals[:, 1:].max() < 1e-8 and vals[2, 5] > 0
+
+
+def test_write_data_from_several_ranks_is_one_complete_file(tmp_path):
+    """Multi-rank write_data: every rank formats its own atoms, ranks > 0 hand theirs over
+    through part files, rank 0 writes ONE file with the global box and all atoms (the
+    reference writes rank 0's sub-box and atoms only, read_data.h:385-421).  Played here as
+    three sequential single-rank calls of the same code."""
+    box = (0.0, 9.0)
+    ids, typ, x, v = make_state(600, seed=21, box=box)
+    write_data_file(tmp_path / "in.data", ids, typ, x, v, box, 2)
+    slabs = [(0.0, 3.0), (3.0, 6.0), (6.0, 9.0)]          # 3 ranks along x
+    for rank in (2, 1, 0):                                 # rank 0 last: it assembles
+        lo, hi = slabs[rank]
+        p = tool("data", tmp_path / "in.data", tmp_path / "out.data", 17, "atomic", lo, hi, 0, 9, 0, 9, rank, 3)
+        assert p.returncode == 0, p.stderr
+    assert not list(tmp_path.glob("out.data.part*"))       # part files are consumed
+    text = (tmp_path / "out.data").read_text()
+    assert text.splitlines()[2] == "600 atoms"
+    assert text.splitlines()[5] == "0 9 xlo xhi"            # the GLOBAL box
+    i2, t2, x2, iv, v2 = parse_data_file(text)
+    order = np.concatenate([np.flatnonzero((x[:, 0] >= lo) & (x[:, 0] < hi)) for lo, hi in slabs])
+    assert len(order) == 600
+    assert np.array_equal(i2, ids[order]) and np.array_equal(iv, ids[order])   # rank order, file order inside
+    assert np.array_equal(x2, x[order]) and np.array_equal(v2, v[order]) and np.array_equal(t2, typ[order])
