@@ -407,10 +407,9 @@ def main():
         traffic = tr.get(key)
     except Exception:
         pass
-    group = int(os.environ.get("CBMD_NB_GROUP", "1"))
     gather = int(os.environ.get("CBMD_GATHER", "1"))
-    kname = ("k_force_half" if args.half else "k_force_full") + (
-        "_g8" if group == 8 else ("_tex" if gather == 1 and not args.half else ""))
+    kname = "k_force_half" if args.half else ("k_force_full<1,...> (xy LDG.128 + z TEX)" if gather == 1
+                                              else "k_force_full<0,...> (32-byte records)")
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": traffic,
@@ -435,9 +434,7 @@ def main():
     if n == 1 and not args.no_ab:
         # A/B of the force kernel's gather path / sweep shape on the headline workload
         # (DESIGN.md 3.1): 32-byte records by LDG.256 (no texture path), and 8 lanes per atom
-        for label, env in (("A/B gather=0 (32-byte records, LDG.256 only)", {"CBMD_GATHER": "0"}),
-                           ("A/B nb_group=8 (eight lanes per atom, quad-grouped table)",
-                            {"CBMD_NB_GROUP": "8"})):
+        for label, env in (("A/B gather=0 (32-byte records, LDG.256 only)", {"CBMD_GATHER": "0"}),):
             os.environ.update(env)
             try:
                 s1 = build_sim(args, args.cells, args.half, 1, 0, None, local)

@@ -17,18 +17,20 @@ void cbmd_exclusive_scan_int( cbmd_ctx *ctx, int *data, int n )
     // in place over n+1 entries (data[n] must be 0 on entry) so data[n] = total
     size_t tmp = 0;
     CBMD_CUDA( cub::DeviceScan::ExclusiveSum( nullptr, tmp, data, data, n + 1, ctx->stream ) );
-    static thread_local void *d_tmp = nullptr;
-    static thread_local size_t d_tmp_bytes = 0;
-    if ( tmp > d_tmp_bytes )
+    // CUB temp storage belongs to the context (its device, its stream): contexts on other
+    // devices or streams of the same thread must not share it; freed by cbmd_destroy
+    if ( tmp > ctx->scan_tmp_bytes )
     {
-        if ( d_tmp )
+        if ( ctx->scan_tmp )
         {
             CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );
-            CBMD_CUDA( cudaFree( d_tmp ) );
+            CBMD_CUDA( cudaFree( ctx->scan_tmp ) );
         }
-        d_tmp_bytes = tmp + ( 1 << 16 );
-        CBMD_CUDA( cudaMalloc( &d_tmp, d_tmp_bytes ) );
+        ctx->scan_tmp = nullptr;
+        ctx->scan_tmp_bytes = tmp + ( 1 << 16 );
+        CBMD_CUDA( cudaMalloc( &ctx->scan_tmp, ctx->scan_tmp_bytes ) );
     }
+    void *d_tmp = ctx->scan_tmp;
     CBMD_CUDA( cub::DeviceScan::ExclusiveSum( d_tmp, tmp, data, data, n + 1, ctx->stream ) );
     ctx->launches += 2;
 }

@@ -544,8 +544,7 @@ extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
 __global__ void __launch_bounds__( 256 )
     k_halo_update_flat( XT *__restrict__ xt, int n_local, int n_ghost,
                         const int *__restrict__ owner, const unsigned char *__restrict__ image,
-                        double Lx, double Ly, double Lz, double2 *__restrict__ xy,
-                        double *__restrict__ zs )
+                        double Lx, double Ly, double Lz, const MirrorPtrs mir )
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if ( g >= n_ghost )
@@ -560,11 +559,7 @@ __global__ void __launch_bounds__( 256 )
     if ( iz )
         r.z += ( iz == 1u ? Lz : -Lz );
     xt[n_local + g] = r;
-    if ( xy ) // split mirror for the texture-assisted force gather (cbmd_force.cu)
-    {
-        xy[n_local + g] = make_double2( r.x, r.y );
-        zs[n_local + g] = r.z;
-    }
+    mirror_store( mir, n_local + g, r ); // gather mirror of the force sweeps (cbmd_force.cu)
 }
 
 __global__ void __launch_bounds__( 256 )
@@ -599,7 +594,7 @@ extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
         const bool live = cbmd_mirror_live( ctx );
         k_halo_update_flat<<<div_up( ctx->n_ghost, 256 ), 256, 0, ctx->stream>>>(
             ctx->xt, ctx->n_local, ctx->n_ghost, ctx->ghost_owner, ctx->ghost_image, ctx->gext[0],
-            ctx->gext[1], ctx->gext[2], live ? ctx->xy : nullptr, live ? ctx->zs : nullptr );
+            ctx->gext[1], ctx->gext[2], cbmd_mirror_ptrs( ctx ) );
         CBMD_LAUNCH_CHECK( ctx );
         if ( live )
             ctx->mirror_ghost_epoch = ctx->epoch;

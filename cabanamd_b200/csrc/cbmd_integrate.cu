@@ -13,7 +13,7 @@
 __global__ void __launch_bounds__( 256 )
     k_integrate_initial( XT *__restrict__ xt, double *__restrict__ v, const double *__restrict__ f,
                          int cap, int n, const __grid_constant__ MassTable mt, double dtv,
-                         double2 *__restrict__ xy, double *__restrict__ zs )
+                         const MirrorPtrs mir )
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if ( i >= n )
@@ -32,11 +32,7 @@ __global__ void __launch_bounds__( 256 )
     v[(size_t)cap + i] = vy;
     v[2 * (size_t)cap + i] = vz;
     xt[i] = r;
-    if ( xy ) // split mirror for the texture-assisted force gather (cbmd_force.cu)
-    {
-        xy[i] = make_double2( r.x, r.y );
-        zs[i] = r.z;
-    }
+    mirror_store( mir, i, r ); // gather mirror of the force sweeps (cbmd_force.cu)
 }
 
 __global__ void __launch_bounds__( 256 )
@@ -60,7 +56,7 @@ __global__ void __launch_bounds__( 256 )
     k_integrate_final_initial( XT *__restrict__ xt, double *__restrict__ v,
                                const double *__restrict__ f, int cap, int n,
                                const __grid_constant__ MassTable mt, double dtv,
-                               double2 *__restrict__ xy, double *__restrict__ zs )
+                               const MirrorPtrs mir )
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if ( i >= n )
@@ -80,11 +76,7 @@ __global__ void __launch_bounds__( 256 )
     v[(size_t)cap + i] = vy;
     v[2 * (size_t)cap + i] = vz;
     xt[i] = r;
-    if ( xy )
-    {
-        xy[i] = make_double2( r.x, r.y );
-        zs[i] = r.z;
-    }
+    mirror_store( mir, i, r );
 }
 
 void cbmd_materialize_final( cbmd_ctx *ctx )
@@ -110,20 +102,22 @@ extern "C" int cbmd_integrate_initial( cbmd_ctx *ctx )
     cbmd_materialize_zero_force( ctx );
     cbmd_bump_epoch( ctx, true, false );
     const int n = ctx->n_local;
+    CBMD_REQUIRE( ctx->max_type < ctx->ntypes,
+                  "an atom has type " + std::to_string( ctx->max_type ) + " (0-based) but cbmd_set_mass defined " +
+                      std::to_string( ctx->ntypes ) + " type(s)" );
     const bool fused = ctx->final_pending;
     ctx->final_pending = false;
     if ( n > 0 )
     {
         // every owned position is rewritten here: keep the force kernel's split mirror current
         const bool live = cbmd_mirror_live( ctx );
-        double2 *xy = live ? ctx->xy : nullptr;
-        double *zs = live ? ctx->zs : nullptr;
+        const MirrorPtrs mir = cbmd_mirror_ptrs( ctx );
         if ( fused )
             k_integrate_final_initial<<<div_up( n, 256 ), 256, 0, ctx->stream>>>(
-                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt, xy, zs );
+                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt, mir );
         else
             k_integrate_initial<<<div_up( n, 256 ), 256, 0, ctx->stream>>>(
-                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt, xy, zs );
+                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt, mir );
         CBMD_LAUNCH_CHECK( ctx );
         if ( live )
             ctx->mirror_owned_epoch = ctx->epoch;

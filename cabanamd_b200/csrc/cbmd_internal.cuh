@@ -37,6 +37,32 @@ struct LJTable
     double eshift[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
 };
 
+// FP32 copy of the pair tables for the precision-32 force sweeps
+struct LJTableF
+{
+    int ntypes;
+    float lj1[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+    float lj2[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+    float cutsq[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+    float e1[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+    float e2[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+    float eshift[CBMD_MAX_TYPES * CBMD_MAX_TYPES];
+};
+
+// Gather mirror of the positions for the full-list force sweeps (cbmd_force.cu).  Every kernel
+// that writes positions (integrator, one-rank halo refresh, re-split) stores whichever parts
+// are allocated:
+//   kind 1 (FP64, one type):   xy = {x,y} packed (LDG.128)  +  zs = z (8-byte texels, TEX)
+//   kind 2 (FP64, multi-type): xy                           +  zt = {z, type bits} (16-byte texels)
+//   kind 3 (FP32, option "precision" 32): xf = {x,y,z,type bits} as floats (LDG.128)
+struct MirrorPtrs
+{
+    double2 *xy;
+    double *zs;
+    double2 *zt;
+    float4 *xf;
+};
+
 struct MassTable
 {
     double dtfm[CBMD_MAX_TYPES]; // dtf / mass[type]
@@ -63,6 +89,7 @@ struct cbmd_ctx
     // units / tables
     double boltz = 1.0, mvv2e = 1.0, dt = 0.005;
     int ntypes = 1;
+    int max_type = 0; // largest atom type uploaded so far (0-based); checked against the tables
     MassTable mass;
     LJTable lj;
 
@@ -78,18 +105,19 @@ struct cbmd_ctx
     double *f = nullptr, *f_alt = nullptr; // SoA [3][cap]
     int *id = nullptr, *id_alt = nullptr;
     double *q = nullptr, *q_alt = nullptr;
-    // split mirror of the positions for the texture-assisted gather of the single-type
-    // full-list force kernel (cbmd_force.cu): x,y packed as double2 (LDG.128 through the LSU
-    // pipe), z as a plain array read through the TEX path (8-byte texels)
-    double2 *xy = nullptr;
-    double *zs = nullptr;
-    cudaTextureObject_t tex_z = 0;
-    int mirror_cap = 0;
+    // gather mirror of the positions (see MirrorPtrs); one allocation, re-made when the
+    // capacity or the wanted kind changes
+    MirrorPtrs mir = { nullptr, nullptr, nullptr, nullptr };
+    void *mirror_buf = nullptr;
+    int mirror_kind = 0, mirror_cap = 0;
+    cudaTextureObject_t tex_z = 0; // zs (8-byte texels) or zt (16-byte texels), by kind
     // value of `epoch` at which the owned / ghost part of the mirror was last consistent with
     // xt; the integrator and the one-rank halo refresh write the mirror themselves, anything
     // else that moves atoms leaves it stale and cbmd_force_lj re-splits that part
     uint64_t mirror_owned_epoch = 0, mirror_ghost_epoch = 0;
-    int gather_mode = 1; // option "gather": 0 = 32-byte records by LDG.256, 1 = xy LDG.128 + z TEX
+    int gather_mode = 1; // option "gather": 0 = 32-byte records by LDG.256, 1 = mirror (split / FP32) gathers
+    int precision = 64;  // option "precision": 64, or 32 = FP32 pair arithmetic on float positions (full lists)
+    LJTableF ljf;
     bool f_zero_pending = false; // deferred deep_copy(f,0): fused into the full-list force kernel
     // deferred Integrator::final_integrate: when the next call is initial_integrate the two
     // half kicks and the drift run as ONE streaming kernel (same roundings, 43 % less traffic);
@@ -119,12 +147,11 @@ struct cbmd_ctx
 
     // Verlet list, padded 2-D table; addressing by nb_entry() below
     int nb_half = 0, nb_layout = 0;
-    int nb_group = 1;      // lanes sharing one atom in the pair sweeps (layout of the CURRENT list)
-    int nb_group_next = 1; // option "nb_group" (1 or 8): takes effect at the next build
-    int nb_rows = 0;   // row capacity (max_neigh_guess in effect)
+    int nb_rows = 0;   // row capacity: max_neigh_guess in effect rounded up to a multiple of 4
     int nb_stride = 0; // >= n_local, multiple of 32
     int nb_n = 0;      // n_local at build time
     int nb_ntot = 0;
+    cudaTextureObject_t tex_nb = 0; // the table as 16-byte texels (index stream of the FP32 sweep)
     int *nb = nullptr;
     size_t nb_alloc = 0;
     int *nb_count = nullptr; // [cap]
@@ -157,6 +184,8 @@ struct cbmd_ctx
     // scratch
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    void *scan_tmp = nullptr; // CUB temp storage of cbmd_exclusive_scan_int
+    size_t scan_tmp_bytes = 0;
     double *d_red = nullptr; // small device reduction buffer
     int *d_flags = nullptr;  // small device int buffer (counters)
     double *h_pinned = nullptr;
@@ -309,10 +338,24 @@ inline void cbmd_bump_epoch( cbmd_ctx *ctx, bool owned_changed, bool ghosts_chan
     if ( g )
         ctx->mirror_ghost_epoch = ctx->epoch;
 }
-// the split mirror is allocated for the current capacity and in use
+// mirror kind the next full-list force launch will want
+inline int cbmd_mirror_wanted( const cbmd_ctx *ctx )
+{
+    if ( ctx->precision == 32 )
+        return 3;
+    if ( ctx->gather_mode != 1 )
+        return 0;
+    return ctx->lj.ntypes == 1 ? 1 : 2;
+}
+// the mirror is allocated for the current capacity and of the kind in use
 inline bool cbmd_mirror_live( const cbmd_ctx *ctx )
 {
-    return ctx->gather_mode == 1 && ctx->xy != nullptr && ctx->mirror_cap == ctx->cap;
+    return ctx->mirror_kind != 0 && ctx->mirror_kind == cbmd_mirror_wanted( ctx ) && ctx->mirror_cap == ctx->cap;
+}
+// pointers for the kernels that write positions: all null unless the mirror is live
+inline MirrorPtrs cbmd_mirror_ptrs( const cbmd_ctx *ctx )
+{
+    return cbmd_mirror_live( ctx ) ? ctx->mir : MirrorPtrs{ nullptr, nullptr, nullptr, nullptr };
 }
 void cbmd_exclusive_scan_int( cbmd_ctx *ctx, int *data, int n ); // in place, data[n] = total
 
@@ -347,37 +390,40 @@ __device__ __forceinline__ int cell_coord( double xv, double mn, double rdx, int
     return c;
 }
 
-// Verlet table layout: tiles of 32 consecutive atoms; neighbour n of atom i sits at
-//   nb[((i >> 5) * rows + n) * 32 + (i & 31)]
-// so a warp of 32 consecutive atoms reads row n as one 128-byte line (coalesced), and
-// everything a warp reads or writes lies in ONE contiguous rows*128-byte block (TLB- and
-// DRAM-page-local, unlike a [rows][n_atoms] table whose rows are megabytes apart).
+// Verlet table layout: tiles of 32 consecutive atoms, rows packed four entries per 16 bytes.
+// With rows4 = rows/4 (rows is a multiple of 4), entries 4k..4k+3 of atom i are the int4
+//   nb4[((i >> 5) * rows4 + k) * 32 + (i & 31)]
+// i.e. neighbour n of atom i is the int at
+//   ((i >> 5) * rows4 + (n >> 2)) * 128 + (i & 31) * 4 + (n & 3).
+// A warp of 32 consecutive atoms reads four entries per lane as ONE coalesced 512-byte request
+// (a quarter of the index-load instructions of a one-entry-per-load table), and everything a
+// warp touches is one contiguous rows*128-byte block (TLB- and DRAM-page-local).  Rows are
+// padded to a multiple of four with the atom's own index (rejected by the sweeps: j != i).
 __host__ __device__ __forceinline__ size_t nb_tile_base( int i, int rows )
 {
-    return ( (size_t)( i >> 5 ) * (size_t)rows ) * 32 + (size_t)( i & 31 );
+    return ( (size_t)( i >> 5 ) * (size_t)( rows >> 2 ) ) * 128 + (size_t)( i & 31 ) * 4;
 }
-
-// Grouped layout (option nb_group == 8, an A/B alternative): the pair sweeps give every atom 8 lanes that walk 8
-// CONSECUTIVE entries of its row at once (4 atoms per warp).  Entries are stored in quads
-// of atoms: with R8 = ceil(rows/8) chunks per row,
-//   nb[(((i >> 2) * R8 + (n >> 3)) * 32) + (i & 3) * 8 + (n & 7)]
-// so chunk r of the four atoms of a quad is one 128-byte line, lane = (i&3)*8 + (n&7), and a
-// quad's chunks are contiguous.  A 32-atom tile is still one contiguous R8*1024-byte block.
-__host__ __device__ __forceinline__ int nb_chunks( int rows ) { return ( rows + 7 ) >> 3; }
-__host__ __device__ __forceinline__ size_t nb_quad_base( int i, int rows )
+// element offset of neighbour n of atom i
+__host__ __device__ __forceinline__ size_t nb_entry( int i, int n, int rows )
 {
-    return ( (size_t)( i >> 2 ) * (size_t)nb_chunks( rows ) ) * 32 + (size_t)( i & 3 ) * 8;
-}
-// element offset of neighbour n of atom i in either layout
-__host__ __device__ __forceinline__ size_t nb_entry( int group, int i, int n, int rows )
-{
-    return group == 8 ? nb_quad_base( i, rows ) + (size_t)( n >> 3 ) * 32 + (size_t)( n & 7 )
-                      : nb_tile_base( i, rows ) + (size_t)n * 32;
+    return nb_tile_base( i, rows ) + (size_t)( n >> 2 ) * 128 + (size_t)( n & 3 );
 }
 // table elements needed for `stride` (multiple of 32) atoms
-__host__ __device__ __forceinline__ size_t nb_table_size( int group, int stride, int rows )
+__host__ __device__ __forceinline__ size_t nb_table_size( int stride, int rows ) { return (size_t)stride * (size_t)rows; }
+
+// store a position into whichever mirror parts exist (kernels that write xt call this)
+__device__ __forceinline__ void mirror_store( const MirrorPtrs &m, int i, const XT &r )
 {
-    return (size_t)stride * (size_t)( group == 8 ? 8 * nb_chunks( rows ) : rows );
+    if ( m.xy )
+    {
+        m.xy[i] = make_double2( r.x, r.y );
+        if ( m.zs )
+            m.zs[i] = r.z;
+        if ( m.zt )
+            m.zt[i] = make_double2( r.z, __longlong_as_double( r.t ) );
+    }
+    if ( m.xf )
+        m.xf[i] = make_float4( (float)r.x, (float)r.y, (float)r.z, __int_as_float( (int)r.t ) );
 }
 
 struct GridDesc

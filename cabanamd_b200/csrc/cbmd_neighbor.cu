@@ -7,14 +7,13 @@
 // evaluated un-contracted, left to right); Full: i != j; Half: i != j and
 // (xj>xi || (xj==xi && (yj>yi || (yj==yi && zj>zi)))); ghost rows are empty.
 //
-// Device layout: padded 2-D table, addressed by nb_entry() (cbmd_internal.cuh).  Default
-// (nb_group 1): tiles of 32 atoms, neighbour n of atom i at nb[((i>>5)*rows + n)*32 + (i&31)],
-// for the one-lane-per-atom sweeps.  Option nb_group 8: quads of atoms, 8 consecutive entries
-// of each of the 4 atoms per 128-byte line, for the sweeps that give every atom 8 lanes.
-// Either way a warp reads its index stream fully coalesced and a tile's rows are one
-// contiguous block.  The CSR view the reference also offers is produced on demand by
-// cbmd_neigh_get.  Row capacity follows Cabana's 2-D policy: start from
-// max_neigh_guess, and if any row overflows rebuild at 1.1 x the observed maximum.
+// Device layout: padded 2-D table, addressed by nb_entry() (cbmd_internal.cuh): tiles of 32
+// atoms, four entries of a row per 16 bytes, so a warp of the one-lane-per-atom sweeps reads
+// four neighbours per lane as one coalesced 512-byte request and a tile's rows are one
+// contiguous block.  Rows are padded to a multiple of four with the atom's own index.  The
+// CSR view the reference also offers is produced on demand by cbmd_neigh_get.  Row capacity
+// follows Cabana's 2-D policy: start from max_neigh_guess (rounded up to a multiple of four),
+// and if any row overflows rebuild at 1.1 x the observed maximum.
 #include "cbmd_internal.cuh"
 
 void cbmd_build_cell_lists_grid( cbmd_ctx *ctx, const GridDesc &g, int first, int count );
@@ -50,7 +49,7 @@ __device__ __forceinline__ bool half_valid( const XT &a, const XT &b )
 // ---------------------------------------------------------------------------
 // K staged candidates against this lane's atom: FP32 decisions, ONE warp vote for the
 // (rare) exact FP64 re-evaluation, then in-order, branch-free appends to the lane's row.
-template <bool HALF, int K, bool GROUPED>
+template <bool HALF, int K>
 __device__ __forceinline__ void
 sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const XT &xi, float xr,
              float yr, float zr, int i, float r2lo, float r2hi, float tolx, double rsqr,
@@ -96,11 +95,10 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
 #pragma unroll
     for ( int k = 0; k < K; k++ )
     {
-        // predicated store (no branch).  Tiled layout: entry n of this lane's column is 128
-        // bytes further on; grouped layout: 8 consecutive entries per 128-byte chunk line
+        // predicated store (no branch): entries 4k..4k+3 of this lane's row are one int4,
+        // consecutive int4s of the row are 512 bytes apart
         const int st = ( ok[k] && count < nb_rows ) ? 1 : 0;
-        const unsigned off = GROUPED ? ( ( (unsigned)count >> 3 ) << 7 ) + ( ( (unsigned)count & 7u ) << 2 )
-                                     : (unsigned)count << 7;
+        const unsigned off = ( ( (unsigned)count >> 2 ) << 9 ) + ( ( (unsigned)count & 3u ) << 2 );
         char *dst = row0 + (unsigned long long)off;
         asm volatile( "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b32 [%0], %1;\n\t}"
                       :
@@ -114,7 +112,7 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
 #define NB_THREADS ( 32 * NBC )
 #define NB_STAGE 1280 // candidates per staging chunk (20 KB)
 
-template <bool HALF, bool GROUPED>
+template <bool HALF>
 __global__ void __launch_bounds__( NB_THREADS )
     k_neigh_build( const XT *__restrict__ xt, int n_local, GridDesc g,
                    const int *__restrict__ cell_start, const int *__restrict__ cell_atoms,
@@ -228,7 +226,7 @@ __global__ void __launch_bounds__( NB_THREADS )
             xi = ld_xt( xt + i );
         const float xr = active ? (float)( xi.x - ox ) : 0.f, yr = active ? (float)( xi.y - oy ) : 0.f,
                     zr = active ? (float)( xi.z - oz ) : 0.f;
-        char *const row0 = (char *)( nb + nb_entry( GROUPED ? 8 : 1, active ? i : 0, 0, nb_rows ) );
+        char *const row0 = (char *)( nb + nb_tile_base( active ? i : 0, nb_rows ) );
         int count = 0;
 
         for ( int chunk = 0; chunk < total; chunk += NB_STAGE )
@@ -285,15 +283,20 @@ __global__ void __launch_bounds__( NB_THREADS )
                 const int n4 = ( e - b ) >> 2;
                 const float4 *cp = cand + b;
                 for ( int q = 0; q < n4; q++, cp += 4 )
-                    sweep_group<HALF, 4, GROUPED>( cp, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx, rsqr,
+                    sweep_group<HALF, 4>( cp, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx, rsqr,
                                                    row0, nb_rows, count );
                 for ( int t = b + 4 * n4; t < e; t++ )
-                    sweep_group<HALF, 1, GROUPED>( cand + t, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx,
+                    sweep_group<HALF, 1>( cand + t, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx,
                                                    rsqr, row0, nb_rows, count );
             }
         }
         if ( active )
+        {
             nb_count[i] = count;
+            // pad the row to a multiple of four with the atom itself (never a neighbour)
+            for ( int k = count; k < min( ( count + 3 ) & ~3, nb_rows ); k++ )
+                *(int *)( row0 + ( ( (unsigned)k >> 2 ) << 9 ) + ( ( (unsigned)k & 3u ) << 2 ) ) = i;
+        }
         int mx = count;
         for ( int o = 16; o > 0; o >>= 1 )
             mx = max( mx, __shfl_xor_sync( 0xffffffffu, mx, o ) );
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__( NB_THREADS )
 }
 
 __global__ void __launch_bounds__( 256 )
-    k_nb_to_csr( const int *__restrict__ nb, int nb_rows, int nb_group,
+    k_nb_to_csr( const int *__restrict__ nb, int nb_rows,
                  const int *__restrict__ nb_count, const int64_t *__restrict__ offsets, int n_local,
                  int *__restrict__ csr )
 {
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__( 256 )
     const int c = nb_count[i];
     const int64_t o = offsets[i];
     for ( int n = 0; n < c; n++ )
-        csr[o + n] = nb[nb_entry( nb_group, i, n, nb_rows )];
+        csr[o + n] = nb[nb_entry( i, n, nb_rows )];
 }
 
 // ---------------------------------------------------------------------------
@@ -430,12 +433,11 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
     cbmd_build_cell_lists_grid( ctx, g, 0, n_total );
 
     ctx->nb_half = half ? 1 : 0;
-    ctx->nb_group = ctx->nb_group_next;
     ctx->nb_layout = layout;
     ctx->nb_rcut = rcut;
     ctx->nb_n = n_local;
     ctx->nb_ntot = n_total;
-    int rows = max_neigh_guess > 0 ? max_neigh_guess : 1;
+    int rows = ( ( max_neigh_guess > 0 ? max_neigh_guess : 1 ) + 3 ) & ~3;
     const int stride = ( n_local + 31 ) & ~31;
     const double rsqr = rcut * rcut;
     const double3 centre = make_double3( 0.5 * ( ctx->llo[0] + ctx->lhi[0] ),
@@ -447,17 +449,33 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
     int observed = 0;
     for ( int attempt = 0; attempt < 3; attempt++ )
     {
-        const size_t need = nb_table_size( ctx->nb_group, stride > 0 ? stride : 32, rows );
+        const size_t need = nb_table_size( stride > 0 ? stride : 32, rows );
         if ( need > ctx->nb_alloc )
         {
             if ( ctx->nb )
             {
                 CBMD_CUDA( cudaStreamSynchronize( s ) );
+                if ( ctx->tex_nb )
+                    CBMD_CUDA( cudaDestroyTextureObject( ctx->tex_nb ) );
+                ctx->tex_nb = 0;
                 CBMD_CUDA( cudaFree( ctx->nb ) );
             }
             ctx->nb = nullptr;
-            ctx->nb_alloc = need + need / 8;
+            ctx->nb_alloc = ( need + need / 8 + 3 ) & ~(size_t)3;
             CBMD_CUDA( cudaMalloc( &ctx->nb, ctx->nb_alloc * sizeof( int ) ) );
+            // the table as 16-byte texels: index stream of the FP32 sweep (a linear texture
+            // addresses at most 2^27 texels; larger tables are read through LDG.128)
+            if ( ctx->nb_alloc / 4 <= ( (size_t)1 << 27 ) )
+            {
+                cudaResourceDesc rd = {};
+                rd.resType = cudaResourceTypeLinear;
+                rd.res.linear.devPtr = ctx->nb;
+                rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+                rd.res.linear.sizeInBytes = ctx->nb_alloc * sizeof( int );
+                cudaTextureDesc td = {};
+                td.readMode = cudaReadModeElementType;
+                CBMD_CUDA( cudaCreateTextureObject( &ctx->tex_nb, &rd, &td, nullptr ) );
+            }
         }
         ctx->nb_rows = rows;
         ctx->nb_stride = stride;
@@ -465,19 +483,14 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
         if ( n_local > 0 )
         {
             const int blocks = g.n[0] * g.n[1] * ( ( g.n[2] + NBC - 1 ) / NBC );
-#define NB_LAUNCH( H, G )                                                                         \
-    k_neigh_build<H, G><<<blocks, NB_THREADS, 0, s>>>( ctx->xt, n_local, g, ctx->cell_start,      \
-                                                       ctx->cell_atoms, rsqr, centre, ctx->nb,    \
-                                                       stride, rows, ctx->nb_count, d_max )
-            const bool grouped = ctx->nb_group == 8;
-            if ( half && grouped )
-                NB_LAUNCH( true, true );
-            else if ( half )
-                NB_LAUNCH( true, false );
-            else if ( grouped )
-                NB_LAUNCH( false, true );
+#define NB_LAUNCH( H )                                                                            \
+    k_neigh_build<H><<<blocks, NB_THREADS, 0, s>>>( ctx->xt, n_local, g, ctx->cell_start,         \
+                                                    ctx->cell_atoms, rsqr, centre, ctx->nb, stride, \
+                                                    rows, ctx->nb_count, d_max )
+            if ( half )
+                NB_LAUNCH( true );
             else
-                NB_LAUNCH( false, false );
+                NB_LAUNCH( false );
 #undef NB_LAUNCH
             CBMD_LAUNCH_CHECK( ctx );
         }
@@ -491,6 +504,7 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
         rows = (int)( observed * 1.1 ); // [Cabana] 2-D regrow + refill
         if ( rows < observed )
             rows = observed;
+        rows = ( rows + 3 ) & ~3;
         CBMD_REQUIRE( attempt < 2, "neighbour list did not converge" );
     }
     ctx->nb_max = observed;
@@ -533,8 +547,8 @@ extern "C" int cbmd_neigh_get( cbmd_ctx *ctx, int *counts, int64_t *offsets, int
         int *d_csr = (int *)( st + ob );
         CBMD_CUDA( cudaMemcpyAsync( d_off, ho.data(), (size_t)( n_local + 1 ) * sizeof( int64_t ),
                                     cudaMemcpyHostToDevice, s ) );
-        k_nb_to_csr<<<div_up( n_local, 256 ), 256, 0, s>>>( ctx->nb, ctx->nb_rows, ctx->nb_group,
-                                                            ctx->nb_count, d_off, n_local, d_csr );
+        k_nb_to_csr<<<div_up( n_local, 256 ), 256, 0, s>>>( ctx->nb, ctx->nb_rows, ctx->nb_count, d_off,
+                                                            n_local, d_csr );
         CBMD_LAUNCH_CHECK( ctx );
         CBMD_CUDA( cudaMemcpyAsync( neighbors, d_csr, (size_t)ho[n_local] * sizeof( int ),
                                     cudaMemcpyDeviceToHost, s ) );
@@ -543,14 +557,14 @@ extern "C" int cbmd_neigh_get( cbmd_ctx *ctx, int *counts, int64_t *offsets, int
     CBMD_API_END
 }
 
-extern "C" int64_t cbmd_table_offset( int nb_group, int atom, int n, int row_capacity )
+extern "C" int64_t cbmd_table_offset( int atom, int n, int row_capacity )
 {
-    return (int64_t)nb_entry( nb_group == 8 ? 8 : 1, atom, n, row_capacity );
+    return (int64_t)nb_entry( atom, n, ( row_capacity + 3 ) & ~3 );
 }
 
-extern "C" int64_t cbmd_table_size( int nb_group, int n_atoms, int row_capacity )
+extern "C" int64_t cbmd_table_size( int n_atoms, int row_capacity )
 {
-    return (int64_t)nb_table_size( nb_group == 8 ? 8 : 1, ( n_atoms + 31 ) & ~31, row_capacity );
+    return (int64_t)nb_table_size( ( n_atoms + 31 ) & ~31, ( row_capacity + 3 ) & ~3 );
 }
 
 extern "C" int cbmd_neigh_sizes( cbmd_ctx *ctx, int64_t *total, int *max_neigh )

@@ -104,8 +104,11 @@ void *cbmd_scratch( cbmd_ctx *ctx, size_t bytes )
 // ---------------------------------------------------------------------------
 // pack / unpack kernels between the reference's [n][3] slices and the device layout
 // ---------------------------------------------------------------------------
+// type_range[0] / [1] collect the smallest / largest type seen (validated by the host:
+// the kernels index per-type tables of CBMD_MAX_TYPES entries with it)
 __global__ void k_pack_xt( XT *__restrict__ xt, const double *__restrict__ x3,
-                           const int *__restrict__ type, int first, int n )
+                           const int *__restrict__ type, int first, int n,
+                           int *__restrict__ type_range )
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if ( i >= n )
@@ -114,8 +117,14 @@ __global__ void k_pack_xt( XT *__restrict__ xt, const double *__restrict__ x3,
     r.x = x3[3 * (size_t)i];
     r.y = x3[3 * (size_t)i + 1];
     r.z = x3[3 * (size_t)i + 2];
-    r.t = type ? type[i] : 0;
+    const int t = type ? type[i] : 0;
+    r.t = t;
     xt[first + i] = r;
+    if ( t != 0 )
+    {
+        atomicMin( type_range, t );
+        atomicMax( type_range + 1, t );
+    }
 }
 
 __global__ void k_unpack_xt( const XT *__restrict__ xt, double *__restrict__ x3,
@@ -216,8 +225,8 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
             ctx->overlap = atoi( e );
         if ( const char *e = getenv( "CBMD_GATHER" ) ) // A/B switch: 0 = 32-byte records by LDG.256
             ctx->gather_mode = atoi( e ) == 0 ? 0 : 1;
-        if ( const char *e = getenv( "CBMD_NB_GROUP" ) ) // A/B switch: 8 = eight lanes per atom
-            ctx->nb_group_next = atoi( e ) == 8 ? 8 : 1;
+        if ( const char *e = getenv( "CBMD_PRECISION" ) ) // 32 = FP32 pair arithmetic (full lists)
+            ctx->precision = atoi( e ) == 32 ? 32 : 64;
         CBMD_CUDA( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
         {
             int lo = 0, hi = 0; // comm stream gets the highest priority so its small kernels
@@ -270,17 +279,17 @@ extern "C" int cbmd_destroy( cbmd_ctx *ctx )
     }
     if ( ctx->tex_z )
         cudaDestroyTextureObject( ctx->tex_z );
-    if ( ctx->xy )
-        cudaFree( ctx->xy );
-    if ( ctx->zs )
-        cudaFree( ctx->zs );
+    if ( ctx->tex_nb )
+        cudaDestroyTextureObject( ctx->tex_nb );
+    if ( ctx->mirror_buf )
+        cudaFree( ctx->mirror_buf );
     void *ptrs[] = { ctx->xt,         ctx->xt_alt,      ctx->v,          ctx->v_alt,
                      ctx->f,          ctx->f_alt,       ctx->id,         ctx->id_alt,
                      ctx->q,          ctx->q_alt,       ctx->cell_start, ctx->cell_cursor,
                      ctx->cell_atoms, ctx->atom_cell,   ctx->perm,       ctx->nb,
                      ctx->nb_count,   ctx->ghost_owner, ctx->ghost_image, ctx->sendbuf,
                      ctx->recvbuf,    ctx->scratch,     ctx->d_red,      ctx->d_flags,
-                     ctx->pe_partial, ctx->tile_list, ctx->tile_flag };
+                     ctx->pe_partial, ctx->tile_list, ctx->tile_flag, ctx->scan_tmp };
     for ( void *p : ptrs )
         if ( p )
             cudaFree( p );
@@ -322,15 +331,19 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
     else if ( n == "gather" )
     {
         if ( (int)value != 0 && (int)value != 1 )
-            throw CbmdError( "gather must be 0 (LDG.256 records) or 1 (xy LDG.128 + z TEX)" );
+            throw CbmdError( "gather must be 0 (32-byte records by LDG.256) or 1 (mirror: xy LDG.128 + z TEX, FP32 float4)" );
         ctx->gather_mode = (int)value;
     }
-    else if ( n == "nb_group" )
+    else if ( n == "precision" )
     {
-        // lanes per atom in the pair sweeps + matching table layout; next cbmd_neigh_build
-        if ( (int)value != 1 && (int)value != 8 )
-            throw CbmdError( "nb_group must be 1 or 8" );
-        ctx->nb_group_next = (int)value;
+        // arithmetic of the full-list pair sweeps: 64 (default), or 32 = the reference's
+        // T_F_FLOAT/T_X_FLOAT = float variant (types.h:133-148) for the force evaluation:
+        // positions rounded to float, FP32 pair terms and per-atom sums; the integration
+        // state (x, v, f arrays) stays FP64
+        if ( (int)value != 32 && (int)value != 64 )
+            throw CbmdError( "precision must be 32 or 64" );
+        ctx->precision = (int)value;
+        ctx->pe_valid = false;
     }
     else
         throw CbmdError( "unknown option: " + n );
@@ -462,8 +475,11 @@ static void upload_rows( cbmd_ctx *ctx, int first, int n, const double *x, const
     CBMD_CUDA( cudaMemcpyAsync( d3, x, b3, cudaMemcpyHostToDevice, s ) );
     if ( type )
         CBMD_CUDA( cudaMemcpyAsync( dt, type, (size_t)n * sizeof( int ), cudaMemcpyHostToDevice, s ) );
-    k_pack_xt<<<div_up( n, tb ), tb, 0, s>>>( ctx->xt, d3, type ? dt : nullptr, first, n );
+    int *type_range = ctx->d_flags + 20; // {min, max} over the non-zero types of this upload
+    CBMD_CUDA( cudaMemsetAsync( type_range, 0, 2 * sizeof( int ), s ) );
+    k_pack_xt<<<div_up( n, tb ), tb, 0, s>>>( ctx->xt, d3, type ? dt : nullptr, first, n, type_range );
     CBMD_LAUNCH_CHECK( ctx );
+    CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i + 4, type_range, 2 * sizeof( int ), cudaMemcpyDeviceToHost, s ) );
     if ( v )
     {
         CBMD_CUDA( cudaMemcpyAsync( d3, v, b3, cudaMemcpyHostToDevice, s ) );
@@ -495,6 +511,14 @@ static void upload_rows( cbmd_ctx *ctx, int first, int n, const double *x, const
         CBMD_CUDA( cudaMemsetAsync( ctx->q + first, 0, (size_t)n * sizeof( double ), s ) );
     // host buffers may be pageable: make the call synchronous w.r.t. them
     CBMD_CUDA( cudaStreamSynchronize( s ) );
+    // atom types index per-type tables in the kernels (masses, pair coefficients)
+    const int tmin = ctx->h_pinned_i[4], tmax = ctx->h_pinned_i[5];
+    CBMD_REQUIRE( tmin >= 0 && tmax < CBMD_MAX_TYPES,
+                  "atom type outside [0, " + std::to_string( CBMD_MAX_TYPES ) +
+                      ") (0-based; this build supports at most " + std::to_string( CBMD_MAX_TYPES ) +
+                      " atom types): " + std::to_string( tmin < 0 ? tmin : tmax ) );
+    if ( tmax > ctx->max_type )
+        ctx->max_type = tmax;
 }
 
 extern "C" int cbmd_set_atoms( cbmd_ctx *ctx, int n_local, const double *x, const double *v,
@@ -504,6 +528,7 @@ extern "C" int cbmd_set_atoms( cbmd_ctx *ctx, int n_local, const double *x, cons
     CBMD_REQUIRE( n_local >= 0, "negative atom count" );
     ctx->n_local = 0;
     ctx->n_ghost = 0;
+    ctx->max_type = 0;
     cbmd_bump_epoch( ctx, true, true );
     cbmd_ensure_capacity( ctx, n_local );
     ctx->f_zero_pending = false;

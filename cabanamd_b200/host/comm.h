@@ -34,6 +34,7 @@ class Comm
         w.exchange_unique_id( id );
         cbmd_check( cbmd_comm_init( system->ctx, proc_size, proc_rank, proc_size > 1 ? id : nullptr ),
                     "cbmd_comm_init" );
+        w.retire_unique_id();
         set_print_rank( proc_rank == 0 );
     }
 

@@ -210,6 +210,10 @@ void read_atoms( std::istream &file, t_System *s, LocalAtoms &mine )
             inside = inside && p[d] >= lo[d] && p[d] < hi[d];
         if ( !inside )
             continue;
+        if ( type < 1 || ( s->ntypes > 0 && type > s->ntypes ) )
+            throw std::runtime_error( "read_data: atom " + std::to_string( id ) + " has type " +
+                                      std::to_string( type ) + " outside 1.." + std::to_string( s->ntypes ) +
+                                      " ('atom types' of the header)" ); // on whichever rank owns it
         mine.row_of_id[id] = mine.size();
         mine.id.push_back( id );
         mine.type.push_back( type - 1 );

@@ -1,5 +1,8 @@
 #include "world.h"
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -33,13 +36,26 @@ void World::init_from_env()
         id_file = f;
     else
     {
+        // per-user, per-launch name: torchrun's run id (when present) keeps two launches that
+        // reuse a port apart; rank 0 also removes the file once every rank has joined
         const char *port = std::getenv( "MASTER_PORT" );
-        id_file = std::string( "/tmp/cbmd_nccl_id_" ) + ( port ? port : "0" ) + "_" +
-                  std::to_string( nranks );
+        const char *run = std::getenv( "TORCHELASTIC_RUN_ID" );
+        id_file = std::string( "/tmp/cbmd_nccl_id_" ) + std::to_string( (long)getuid() ) + "_" +
+                  ( port ? port : "0" ) + "_" + std::to_string( nranks );
+        if ( run && *run )
+            id_file += std::string( "_" ) + run;
     }
     if ( rank < 0 || rank >= nranks )
         throw std::runtime_error( "World: RANK outside [0, WORLD_SIZE)" );
 }
+
+// file payload: the 128-byte id followed by the publisher's wall-clock time (seconds)
+static long long wall_seconds()
+{
+    return std::chrono::duration_cast<std::chrono::seconds>( std::chrono::system_clock::now().time_since_epoch() )
+        .count();
+}
+static const long long ID_MAX_AGE_S = 300; // a leftover of a crashed earlier launch is ignored
 
 void World::exchange_unique_id( unsigned char id[128] ) const
 {
@@ -52,14 +68,17 @@ void World::exchange_unique_id( unsigned char id[128] ) const
     {
         if ( cbmd_comm_unique_id( id ) != 0 )
             throw std::runtime_error( std::string( "cbmd_comm_unique_id: " ) + cbmd_last_error() );
-        // publish atomically: write a temporary, then rename
-        const std::string tmp = id_file + ".tmp";
-        {
-            std::ofstream o( tmp, std::ios::binary | std::ios::trunc );
-            o.write( reinterpret_cast<const char *>( id ), 128 );
-            if ( !o )
-                throw std::runtime_error( "cannot write " + tmp );
-        }
+        // publish atomically: exclusive temporary (never follows a planted symlink), then rename
+        const std::string tmp = id_file + ".tmp." + std::to_string( (long)getpid() );
+        ::unlink( tmp.c_str() );
+        const int fd = ::open( tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600 );
+        if ( fd < 0 )
+            throw std::runtime_error( "cannot create " + tmp );
+        const long long now = wall_seconds();
+        const bool ok = ::write( fd, id, 128 ) == 128 && ::write( fd, &now, sizeof now ) == (ssize_t)sizeof now;
+        ::close( fd );
+        if ( !ok )
+            throw std::runtime_error( "cannot write " + tmp );
         if ( std::rename( tmp.c_str(), id_file.c_str() ) != 0 )
             throw std::runtime_error( "cannot publish " + id_file );
         return;
@@ -69,13 +88,24 @@ void World::exchange_unique_id( unsigned char id[128] ) const
         std::ifstream in( id_file, std::ios::binary );
         if ( in )
         {
+            long long stamp = 0;
             in.read( reinterpret_cast<char *>( id ), 128 );
-            if ( in.gcount() == 128 )
+            const bool have_id = in.gcount() == 128;
+            in.read( reinterpret_cast<char *>( &stamp ), sizeof stamp );
+            if ( have_id && in.gcount() == (std::streamsize)sizeof stamp && wall_seconds() - stamp <= ID_MAX_AGE_S )
                 return;
         }
         std::this_thread::sleep_for( std::chrono::milliseconds( 10 ) );
     }
     throw std::runtime_error( "timed out waiting for the NCCL unique id in " + id_file );
+}
+
+// rank 0, after cbmd_comm_init has returned (ncclCommInitRank is collective: every rank has
+// read the id by then): a later launch with the same file name must not find this id
+void World::retire_unique_id() const
+{
+    if ( nranks > 1 && rank == 0 )
+        ::unlink( id_file.c_str() );
 }
 
 std::array<int, 3> dims_create( int n )

@@ -20,6 +20,7 @@ struct World
     void init_from_env();
     // rank 0: create + publish the id; others: wait for it.  128 bytes.
     void exchange_unique_id( unsigned char id[128] ) const;
+    void retire_unique_id() const; // rank 0 removes the published id once all ranks have joined
 };
 
 // MPI_Dims_create( n, 3 ): balanced factorisation, non-increasing

@@ -168,18 +168,22 @@ extern "C"
     int cbmd_timing_get( cbmd_ctx *ctx, int bucket, double *ms, int64_t *count );
     int cbmd_timing_reset( cbmd_ctx *ctx );
     /* Layout of the device Verlet table (host arithmetic only, no device needed): element
-     * offset of neighbour n of atom i for nb_group 1 (tiles of 32 atoms) or 8 (quads of atoms,
-     * 8 consecutive entries per 128-byte line), and the table size in elements for n_atoms
-     * rounded up to a multiple of 32.  Lets tests pin the addressing the kernels share. */
-    int64_t cbmd_table_offset( int nb_group, int atom, int n, int row_capacity );
-    int64_t cbmd_table_size( int nb_group, int n_atoms, int row_capacity );
-    /* kernel variant switches (results are identical to round-off; for A/B measurements):
-     *   "gather"   1 (default) single-type full-list force gathers x,y by LDG.128 from a packed
-     *              mirror and z through the texture path; 0 = 32-byte records by LDG.256
-     *   "nb_group" 1 (default) one lane per atom over the 32-atom tiled table; 8 = eight lanes
-     *              per atom over a quad-grouped table (takes effect at the next cbmd_neigh_build)
-     *   "overlap"  1 (default) halo refresh on a second stream under the interior force tiles
-     * Environment overrides read at cbmd_create: CBMD_GATHER, CBMD_NB_GROUP, CBMD_OVERLAP. */
+     * offset of neighbour n of atom i — tiles of 32 atoms, four entries of a row per 16 bytes:
+     * ((i>>5)*rows/4 + (n>>2))*128 + (i&31)*4 + (n&3), rows = row_capacity rounded up to a
+     * multiple of 4 — and the table size in elements for n_atoms rounded up to a multiple of
+     * 32.  Lets tests pin the addressing the kernels share. */
+    int64_t cbmd_table_offset( int atom, int n, int row_capacity );
+    int64_t cbmd_table_size( int n_atoms, int row_capacity );
+    /* kernel variant switches:
+     *   "gather"    1 (default) the FP64 full-list force gathers x,y by LDG.128 from a packed
+     *               mirror and z (multi-type: {z,type}) through the texture path; 0 = 32-byte
+     *               records by LDG.256.  Same arithmetic, bit-identical forces.
+     *   "precision" 64 (default), or 32: the full-list pair sweep runs in FP32 on float
+     *               positions — the reference's T_X_FLOAT/T_F_FLOAT = float variant
+     *               (src/types.h:133-148) for the force evaluation; integration state stays FP64.
+     *               Forces agree with an FP32 evaluation of the same list to ~1e-6 relative.
+     *   "overlap"   1 (default) halo refresh on a second stream under the interior force tiles
+     * Environment overrides read at cbmd_create: CBMD_GATHER, CBMD_PRECISION, CBMD_OVERLAP. */
     int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value );
 
 #ifdef __cplusplus

@@ -516,6 +516,80 @@ inline void force_full( const double *x, const int *type, double *f, int n_local
     }
 }
 
+// The same sweep as the reference evaluates it when built with T_X_FLOAT = T_F_FLOAT = float
+// (types.h:133-148): positions, pair coefficients, pair terms and the per-atom sums are
+// floats (force_lj_cabana_neigh_impl.h:151-203 with the slice value types narrowed); the result
+// is added to the FP64 force array.  Checker for the product's "precision 32" sweep.
+inline void force_full_f32( const double *x, const int *type, double *f, int n_local,
+                            const NeighList &L, const Params &p )
+{
+#pragma omp parallel for schedule( dynamic, 256 )
+    for ( int i = 0; i < n_local; i++ )
+    {
+        const float xi = (float)x[3 * i], yi = (float)x[3 * i + 1], zi = (float)x[3 * i + 2];
+        const int ti = type[i];
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        for ( int64_t k = L.offsets[i]; k < L.offsets[i + 1]; k++ )
+        {
+            const int j = L.neigh[k];
+            const float dx = xi - (float)x[3 * j], dy = yi - (float)x[3 * j + 1],
+                        dz = zi - (float)x[3 * j + 2];
+            const int tj = type[j];
+            const float rsq = dx * dx + dy * dy + dz * dz;
+            if ( rsq < (float)p.cutsq[ti * p.ntypes + tj] )
+            {
+                const float r2inv = 1.0f / rsq;
+                const float r6inv = r2inv * r2inv * r2inv;
+                const float fpair = ( r6inv * ( (float)p.lj1[ti * p.ntypes + tj] * r6inv -
+                                                (float)p.lj2[ti * p.ntypes + tj] ) ) *
+                                    r2inv;
+                fx += dx * fpair;
+                fy += dy * fpair;
+                fz += dz * fpair;
+            }
+        }
+        f[3 * i] += (double)fx;
+        f[3 * i + 1] += (double)fy;
+        f[3 * i + 2] += (double)fz;
+    }
+}
+
+// full-list pair energy of the float build (compute_energy_full, :261-315): float pair terms,
+// float per-atom sums, FP64 sum over atoms
+inline double energy_full_f32( const double *x, const int *type, int n_local, const NeighList &L,
+                               const Params &p )
+{
+    double PE = 0.0;
+#pragma omp parallel for schedule( static ) reduction( + : PE )
+    for ( int i = 0; i < n_local; i++ )
+    {
+        const float xi = (float)x[3 * i], yi = (float)x[3 * i + 1], zi = (float)x[3 * i + 2];
+        const int ti = type[i];
+        float pe = 0.f;
+        for ( int64_t k = L.offsets[i]; k < L.offsets[i + 1]; k++ )
+        {
+            const int j = L.neigh[k];
+            const float dx = xi - (float)x[3 * j], dy = yi - (float)x[3 * j + 1],
+                        dz = zi - (float)x[3 * j + 2];
+            const int tj = type[j];
+            const float rsq = dx * dx + dy * dy + dz * dz;
+            const float cutsq = (float)p.cutsq[ti * p.ntypes + tj];
+            if ( rsq < cutsq )
+            {
+                const float lj1 = (float)p.lj1[ti * p.ntypes + tj], lj2 = (float)p.lj2[ti * p.ntypes + tj];
+                const float r2inv = 1.0f / rsq;
+                const float r6inv = r2inv * r2inv * r2inv;
+                pe += 0.5f * r6inv * ( 0.5f * lj1 * r6inv - lj2 ) / 6.0f;
+                const float r2invc = 1.0f / cutsq;
+                const float r6invc = r2invc * r2invc * r2invc;
+                pe -= 0.5f * r6invc * ( 0.5f * lj1 * r6invc - lj2 ) / 6.0f;
+            }
+        }
+        PE += (double)pe;
+    }
+    return PE;
+}
+
 // Serial on purpose: the j-side updates make the sum order matter and the
 // oracle must be deterministic.  force_lj_cabana_neigh_impl.h:205-259
 inline void force_half( const double *x, const int *type, double *f, int n_local,

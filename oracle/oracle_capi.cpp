@@ -75,6 +75,21 @@ void orc_force_lj( OrcList *l, const double *x, const int *type, double *f, int 
         force_full( x, type, f, n_local, l->L, p );
 }
 
+// full list, float build of the reference (T_X_FLOAT = T_F_FLOAT = float); f accumulated in place
+void orc_force_lj_f32( OrcList *l, const double *x, const int *type, double *f, int n_local,
+                       int ntypes, const double *lj1, const double *lj2, const double *cutsq )
+{
+    Params p = make_params( ntypes, nullptr, lj1, lj2, cutsq );
+    force_full_f32( x, type, f, n_local, l->L, p );
+}
+
+double orc_energy_lj_f32( OrcList *l, const double *x, const int *type, int n_local, int ntypes,
+                          const double *lj1, const double *lj2, const double *cutsq )
+{
+    Params p = make_params( ntypes, nullptr, lj1, lj2, cutsq );
+    return energy_full_f32( x, type, n_local, l->L, p );
+}
+
 double orc_energy_lj( OrcList *l, const double *x, const int *type, int n_local, int half,
                       int corrected, int ntypes, const double *lj1, const double *lj2,
                       const double *cutsq )

@@ -56,6 +56,9 @@ def lib():
     L.orc_force_lj.argtypes = [vp, c_dp, c_ip, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]
     L.orc_energy_lj.argtypes = [vp, c_dp, c_ip, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]
     L.orc_energy_lj.restype = C.c_double
+    L.orc_force_lj_f32.argtypes = [vp, c_dp, c_ip, c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp]
+    L.orc_energy_lj_f32.argtypes = [vp, c_dp, c_ip, C.c_int, C.c_int, c_dp, c_dp, c_dp]
+    L.orc_energy_lj_f32.restype = C.c_double
     L.orc_integrate.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_ip, C.c_int, C.c_int, c_dp,
                                 C.c_double, C.c_double]
     L.orc_binning.argtypes = [c_dp, C.c_int, c_dp, c_dp, C.c_double, C.c_double, C.c_double,
@@ -163,6 +166,25 @@ class NeighList:
                             dp(np.ascontiguousarray(lj1)), dp(np.ascontiguousarray(lj2)),
                             dp(np.ascontiguousarray(cutsq)))
         return f
+
+    def force_f32(self, x, type_, lj1, lj2, cutsq):
+        """Full-list sweep of the reference's float build (T_X_FLOAT = T_F_FLOAT = float)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        type_ = np.ascontiguousarray(type_, dtype=np.int32)
+        f = np.zeros_like(x)
+        nt = lj1.shape[0]
+        self.L.orc_force_lj_f32(self.h, dp(x), ip(type_), dp(f), self.n_local, nt,
+                                dp(np.ascontiguousarray(lj1)), dp(np.ascontiguousarray(lj2)),
+                                dp(np.ascontiguousarray(cutsq)))
+        return f
+
+    def energy_f32(self, x, type_, lj1, lj2, cutsq):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        type_ = np.ascontiguousarray(type_, dtype=np.int32)
+        nt = lj1.shape[0]
+        return self.L.orc_energy_lj_f32(self.h, dp(x), ip(type_), self.n_local, nt,
+                                        dp(np.ascontiguousarray(lj1)), dp(np.ascontiguousarray(lj2)),
+                                        dp(np.ascontiguousarray(cutsq)))
 
     def energy(self, x, type_, half, lj1, lj2, cutsq, corrected=False):
         x = np.ascontiguousarray(x, dtype=np.float64)

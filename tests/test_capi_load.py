@@ -52,43 +52,35 @@ def test_domain_helper_matches_oracle():
     assert dims_create(12) == (3, 2, 2)
 
 
-@pytest.mark.parametrize("group", [1, 8])
 @pytest.mark.parametrize("rows", [1, 7, 8, 50, 97])
-def test_verlet_table_addressing(group, rows):
-    """The table layouts the build, force, energy and CSR-export kernels share (nb_entry in
+def test_verlet_table_addressing(rows):
+    """The table layout the build, force, energy and CSR-export kernels share (nb_entry in
     cbmd_internal.cuh): every (atom, entry) has its own slot inside the table, a 32-atom tile
-    is one contiguous block, and a warp reads its index stream as whole 128-byte lines."""
+    is one contiguous block, and a warp reads four entries per lane as one 512-byte request."""
     import ctypes as C
 
     import numpy as np
 
     L = cb.load_library()
     L.cbmd_table_offset.restype = C.c_int64
-    L.cbmd_table_offset.argtypes = [C.c_int] * 4
+    L.cbmd_table_offset.argtypes = [C.c_int] * 3
     L.cbmd_table_size.restype = C.c_int64
-    L.cbmd_table_size.argtypes = [C.c_int] * 3
+    L.cbmd_table_size.argtypes = [C.c_int] * 2
     n_atoms = 75  # rounds up to 96 = 3 tiles
-    size = L.cbmd_table_size(group, n_atoms, rows)
-    off = np.array([[L.cbmd_table_offset(group, i, n, rows) for n in range(rows)] for i in range(96)])
+    size = L.cbmd_table_size(n_atoms, rows)
+    rows4 = (rows + 3) // 4
+    assert size == 96 * 4 * rows4                                # rows round up to a multiple of 4
+    off = np.array([[L.cbmd_table_offset(i, n, rows) for n in range(rows)] for i in range(96)])
     assert off.min() >= 0 and off.max() < size
     assert len(np.unique(off)) == off.size                       # no two entries share a slot
     block = size // 3
     for t in range(3):                                           # tile = contiguous block
         o = off[32 * t:32 * t + 32]
         assert o.min() >= t * block and o.max() < (t + 1) * block
-    if group == 1:
-        # row n of a tile is one 128-byte line: lane = atom & 31
-        for n in range(rows):
-            assert np.array_equal(off[:32, n] - off[0, n], np.arange(32))
-            assert off[0, n] % 32 == 0
-    else:
-        # chunk r of a quad (4 atoms x 8 entries) is one 128-byte line: lane = (atom&3)*8 + (n&7)
-        for q in range(0, 96, 4):
-            for r in range((rows + 7) // 8):
-                base = off[q, 8 * r] if 8 * r < rows else None
-                for a in range(4):
-                    for g in range(8):
-                        n = 8 * r + g
-                        if n < rows:
-                            assert off[q + a, n] - base == a * 8 + g
-                assert base % 32 == 0
+    # entries 4k..4k+3 of a lane are one aligned int4; the 32 lanes' int4s of group k are
+    # one contiguous 512-byte run: lane = atom & 31
+    for n in range(rows):
+        assert np.array_equal(off[:32, n] - off[0, n], 4 * np.arange(32))
+        assert off[0, n] % 128 == n % 4
+        if n % 4:
+            assert np.array_equal(off[:, n], off[:, n - 1] + 1)

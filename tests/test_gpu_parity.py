@@ -141,14 +141,10 @@ def test_binning_matches_oracle(cb):
     assert np.array_equal(a["id"], d["id"][:n][perm])
 
 
-# (nb_group, gather): default = one lane per atom with the texture-assisted split gather;
-# the 32-byte-record LDG.256 gather; 8 lanes per atom over the quad-grouped table
-SWEEPS = [(1, 1), (1, 0), (8, 0)]
-
-
-@pytest.mark.parametrize("group,gather", SWEEPS)
+# gather paths of the FP64 full-list sweep: 1 = mirror (xy LDG.128 + z TEX), 0 = 32-byte records
+@pytest.mark.parametrize("gather", [1, 0])
 @pytest.mark.parametrize("half", [False, True])
-def test_force_energy_on_oracle_state(cb, half, group, gather):
+def test_force_energy_on_oracle_state(cb, half, gather):
     """Same atoms (owned + ghosts from the oracle's 6-phase build): neighbour sets
     bit-exact, forces <= 1e-10 relative, energy to round-off, for every sweep shape /
     gather path of the force kernel."""
@@ -163,7 +159,6 @@ def test_force_energy_on_oracle_state(cb, half, group, gather):
     ctx.set_domain(dom["llo"], dom["lhi"])
     ctx.set_atoms(d["x"][:n], d["v"][:n], None, d["type"][:n], d["id"][:n])
     ctx.append_ghosts(d["x"][n:], d["type"][n:], d["id"][n:])
-    ctx.set_option("nb_group", group)
     ctx.set_option("gather", gather)
     ctx.neigh_build(2.8, half, 0, 50)
     counts, rows = gpu_rows(ctx)
@@ -190,7 +185,7 @@ def test_force_energy_on_oracle_state(cb, half, group, gather):
     ctx.force(half)
     b = ctx.get_atoms()
     assert np.abs(b["f"] - 2 * a["f"]).max() <= 1e-12 * scale
-    if not half and group == 1:
+    if not half:
         # the two gather paths run the same arithmetic in the same order: identical bits
         ctx.set_option("gather", 1 - gather)
         ctx.zero_force()
@@ -198,8 +193,8 @@ def test_force_energy_on_oracle_state(cb, half, group, gather):
         assert np.array_equal(ctx.get_atoms()["f"], a["f"])
 
 
-@pytest.mark.parametrize("group", [8, 1])
-def test_multitype_force(cb, group):
+@pytest.mark.parametrize("gather", [1, 0])
+def test_multitype_force(cb, gather):
     rng = np.random.default_rng(5)
     s = melted_state((8, 8, 8), 40)
     d = s.get()
@@ -219,7 +214,7 @@ def test_multitype_force(cb, group):
     ctx.set_domain(dom["llo"], dom["lhi"])
     ctx.set_atoms(d["x"][:n], None, None, t[:n])
     ctx.append_ghosts(d["x"][n:], t[n:])
-    ctx.set_option("nb_group", group)
+    ctx.set_option("gather", gather)
     ctx.neigh_build(2.8, False, 0, 90)
     oc, oo, on = s.list()
     ol = O.NeighList().set(n, n + ng, oc, oo, on)
@@ -231,6 +226,101 @@ def test_multitype_force(cb, group):
     pe, _ = ctx.energy(False)
     e_ref = ol.energy(d["x"], t, False, lj1, lj2, cutsq)
     assert abs(pe - e_ref) <= 1e-12 * abs(e_ref)
+    # fused force + energy sweep of the multi-type kernel, and the other gather path: same bits
+    ctx.zero_force()
+    ctx.request_energy()
+    ctx.force(False)
+    pe2, _ = ctx.energy(False)
+    assert abs(pe2 - e_ref) <= 1e-12 * abs(e_ref)
+    assert np.abs(ctx.get_atoms()["f"] - a["f"]).max() <= 1e-13 * np.abs(f_ref).max()
+    ctx.set_option("gather", 1 - gather)
+    ctx.zero_force()
+    ctx.force(False)
+    assert np.array_equal(ctx.get_atoms()["f"], a["f"])
+
+
+FORCE_RTOL_F32 = 1e-5  # north_star: per-atom forces to 1e-5 relative in FP32
+
+
+@pytest.mark.parametrize("ntypes", [1, 3])
+def test_force_fp32_variant_matches_float_oracle(cb, ntypes):
+    """Option precision=32 (the reference's T_X_FLOAT/T_F_FLOAT = float build for the force
+    evaluation, types.h:133-148): float positions, FP32 pair terms and sums.  Checked against
+    the float instantiation of the oracle's full-list sweep on the same list, 1e-5 relative;
+    and against the FP64 sweep, where the difference is the float rounding of the positions."""
+    rng = np.random.default_rng(11)
+    s = melted_state((10, 10, 10), 60, False)
+    d = s.get()
+    n, ng = d["n_local"], d["n_ghost"]
+    dom = s.domain()
+    if ntypes == 1:
+        lj1, lj2, cutsq = s.tables
+        t = np.zeros(n + ng, dtype=np.int32)
+        mass = [2.0]
+    else:
+        t = rng.integers(0, ntypes, size=n + ng).astype(np.int32)
+        lj1 = rng.uniform(20, 60, size=(ntypes, ntypes)); lj1 = (lj1 + lj1.T) / 2
+        lj2 = rng.uniform(10, 30, size=(ntypes, ntypes)); lj2 = (lj2 + lj2.T) / 2
+        cutsq = rng.uniform(4.0, 6.25, size=(ntypes, ntypes)); cutsq = (cutsq + cutsq.T) / 2
+        mass = [1.0, 2.0, 3.0]
+    ctx = cb.Context(0)
+    ctx.set_mass(mass)
+    ctx.set_lj(lj1, lj2, cutsq)
+    ctx.set_domain(dom["llo"], dom["lhi"])
+    ctx.set_atoms(d["x"][:n], None, None, t[:n], d["id"][:n])
+    ctx.append_ghosts(d["x"][n:], t[n:], d["id"][n:])
+    ctx.set_option("precision", 32)
+    ctx.neigh_build(2.8, False, 0, 90)
+    oc, oo, on = s.list()
+    ol = O.NeighList().set(n, n + ng, oc, oo, on)
+    f32 = ol.force_f32(d["x"], t, lj1, lj2, cutsq)
+    f64 = ol.force(d["x"], t, False, lj1, lj2, cutsq)
+    ctx.zero_force()
+    ctx.request_energy()
+    ctx.force(False)
+    a = ctx.get_atoms()
+    scale = np.abs(f32).max()
+    assert np.abs(a["f"][:n] - f32[:n]).max() <= FORCE_RTOL_F32 * scale
+    assert np.all(a["f"][n:] == 0.0)                      # full list: ghost rows untouched
+    # against FP64: only the float rounding of x (2^-24 * |x| ~ 1e-6) and of the sums
+    assert np.abs(a["f"][:n] - f64[:n]).max() <= 2e-3 * np.abs(f64).max()
+    pe, _ = ctx.energy(False)
+    e32 = ol.energy_f32(d["x"], t, lj1, lj2, cutsq)
+    assert abs(pe - e32) <= 1e-5 * abs(e32)
+    # accumulate semantics: a second sweep without zeroing doubles f
+    ctx.force(False)
+    b = ctx.get_atoms()
+    assert np.abs(b["f"] - 2 * a["f"]).max() <= 1e-12 * scale
+    # back to FP64: the 1e-10 bar again on the same context
+    ctx.set_option("precision", 64)
+    ctx.zero_force()
+    ctx.force(False)
+    c = ctx.get_atoms()
+    assert np.abs(c["f"] - f64).max() <= FORCE_RTOL * np.abs(f64).max()
+
+
+def test_fp32_variant_trajectory_conserves_energy(cb):
+    """NVE run with the FP32 force sweep (FP64 integration state): total energy stays within
+    the float force noise, and T/PE track the FP64 run over the first steps."""
+    from cabanamd_b200.harness import Simulation
+
+    ref = O.Sim(mass=[2.0]).create_lattice_fcc(cells=(8, 8, 8))
+    d, dom = ref.get(), ref.domain()
+    out = {}
+    for prec in (64, 32):
+        sim = Simulation(device=0)
+        sim.ctx.set_option("precision", prec)
+        sim.set_box(dom["llo"], dom["lhi"])
+        sim.set_atoms(d["x"], d["v"], d["type"], d["id"])
+        sim.setup()
+        sim.record_thermo()
+        sim.run(200, 10)
+        out[prec] = np.array(sim.thermo)
+    e64 = out[64][:, 2] + out[64][:, 3]
+    e32 = out[32][:, 2] + out[32][:, 3]
+    assert np.abs(e32 - e32[0]).max() < 5e-4               # drift of the FP32-force trajectory
+    assert np.abs(e64 - e64[0]).max() < 5e-4
+    assert np.abs(out[32][:3, 1:] - out[64][:3, 1:]).max() < 1e-5   # same physics at the start
 
 
 def canon(x, ids):
