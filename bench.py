@@ -11,11 +11,14 @@ the reference's thermo output (T, PE, KE) every 10 MD steps, exactly the call or
 CbnMD::run (reference src/cabanamd_impl.h:285-399).  Workload: BASELINE.json
 configs[2], 4 000 000 atoms per GPU (fcc 100^3 cells, rho*=0.8442, rc=2.5, skin 0.3,
 full neighbour list, FP64), which at N=1 is the largest single-GPU configuration;
-configs[1] (1 M atoms, full vs half list) is measured alongside and reported under
-"extra".  Data are synthetic: the deck initialiser's lattice + hashed-RNG velocities,
-melted for 200 untimed MD steps so the timed state is the LJ liquid.
+the other configs ride along under "extra": configs[1] (1 M atoms, full vs half list),
+configs[3] (16.4 M atoms strong scaling + the 1000-step energy-drift check against the
+oracle), configs[4] (rc = 5.0) and the FP32 force variant.  Data are synthetic: the deck
+initialiser's lattice + hashed-RNG velocities, melted for 200 untimed MD steps so the timed
+state is the LJ liquid.
 
-The CPU oracle is only used here for the `cpu_baseline` leg and `--impl reference`.
+The CPU oracle is only used here as the checker / baseline: the `cpu_baseline` leg,
+`--impl reference`, and the parity / drift checks that ride along at N >= 1.
 """
 import argparse
 import json
@@ -45,13 +48,18 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=100, help="fcc cells per dim per GPU (100 -> 4 M atoms)")
     ap.add_argument("--half", action="store_true", help="half neighbour list (Newton 3)")
+    ap.add_argument("--precision", type=int, default=64, choices=[64, 32],
+                    help="arithmetic of the full-list force sweep (32 = FP32 variant)")
     ap.add_argument("--melt", type=int, default=200, help="untimed MD steps before warm-up")
     ap.add_argument("--thermo", type=int, default=10, help="thermo every n MD steps (0 = never)")
-    ap.add_argument("--no-extra", action="store_true", help="skip the configs[1] 1 M-atom legs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[1]/[3]/[4] and FP32 legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-ab", action="store_true", help="skip the A/B legs (gather=0, nb_group=8)")
-    ap.add_argument("--cpu-cells", type=int, default=40, help="cpu_baseline sample: cells per dim")
+    ap.add_argument("--no-ab", action="store_true", help="skip the A/B leg (gather=0)")
+    ap.add_argument("--no-checks", action="store_true", help="skip the parity / drift checks vs the oracle")
+    ap.add_argument("--cpu-cells", type=int, default=63, help="cpu_baseline sample: cells per dim")
+    ap.add_argument("--strong-cells", type=int, default=160, help="configs[3]: global fcc cells per dim")
+    ap.add_argument("--strong-steps", type=int, default=1000, help="configs[3]: MD steps")
     ap.add_argument("--cutoff", type=float, default=2.5)
     ap.add_argument("--guess", type=int, default=50)
     return ap.parse_args()
@@ -126,22 +134,35 @@ def local_lattice(sim, cells_global, a):
     return np.ascontiguousarray(x[m])
 
 
-def build_sim(args, cells_per_gpu, half, nranks, rank, uid, device, temp=1.4, seed=87287):
+def build_sim(args, cells_per_gpu, half, nranks, rank, uid, device, temp=1.4, seed=87287,
+              cells_global=None, fast_velocities=False):
+    """One rank of the deck's initial state.  cells_global (3-tuple) overrides the weak-scaling
+    cells_per_gpu * grid; fast_velocities swaps the reference's hashed per-atom RNG (28 hash
+    rounds per atom, vectorised numpy) for a seeded numpy draw — same distribution, only for
+    throughput-only legs on very large systems."""
     from cabanamd_b200.capi import dims_create
     from cabanamd_b200.harness import Simulation, create_velocities
 
     grid = dims_create(nranks)
-    cells_global = tuple(cells_per_gpu * g for g in grid)
+    if cells_global is None:
+        cells_global = tuple(cells_per_gpu * g for g in grid)
     a = (4.0 / 0.8442) ** (1.0 / 3.0)
     sim = Simulation(device=device, mass=(2.0,), cut=args.cutoff, skin=0.3, half=half,
                      exchange_rate=MD_PER_STEP, max_neigh_guess=args.guess, nranks=nranks,
-                     rank=rank, uid=uid)
+                     rank=rank, uid=uid, precision=getattr(args, "precision", 64))
     sim.set_box([0.0] * 3, [a * c for c in cells_global])
     x = local_lattice(sim, cells_global, a)
     t = np.zeros(len(x), dtype=np.int32)
     n_before = sim.ctx.scan_sum_int(len(x)) - len(x) if nranks > 1 else 0
     ids = np.arange(1, len(x) + 1, dtype=np.int32) + n_before
-    v = create_velocities(sim, x, t, temp, seed)
+    if fast_velocities:
+        v = (np.random.default_rng(seed + rank).random((len(x), 3)) - 0.5) / np.sqrt(2.0)
+        tot = np.array([2.0 * len(x), *(2.0 * v).sum(0)])
+        if nranks > 1:
+            tot = np.array([sim.ctx.reduce_sum(q) for q in tot])
+        v = v - tot[1:] / tot[0]
+    else:
+        v = create_velocities(sim, x, t, temp, seed)
     sim.set_atoms(x, v, t, ids)
     # rescale to the target temperature (inputFile_impl.h:851-865)
     T = sim.temperature()
@@ -151,8 +172,8 @@ def build_sim(args, cells_per_gpu, half, nranks, rank, uid, device, temp=1.4, se
     return sim
 
 
-def timed_steps(sim, k, thermo, dist_ctx):
-    """K bench steps bracketed by barrier + synchronize, CUDA events on the context
+def timed_steps(sim, md_steps, thermo, dist_ctx):
+    """md_steps MD steps bracketed by barrier + synchronize, CUDA events on the context
     stream; returns seconds (max over ranks)."""
     import torch
 
@@ -163,7 +184,7 @@ def timed_steps(sim, k, thermo, dist_ctx):
     sim.ctx.sync()
     torch.cuda.synchronize()
     e0.record(stream)
-    sim.run(k * MD_PER_STEP, thermo)
+    sim.run(md_steps, thermo)
     sim.ctx.sync()  # also applies the deferred final_integrate of the last step
     e1.record(stream)
     torch.cuda.synchronize()
@@ -179,38 +200,36 @@ def barrier(dist_ctx):
         dist.barrier()
 
 
-def max_over_ranks(val, dist_ctx):
+def _reduce(val, dist_ctx, op):
     if not dist_ctx:
         return val
     import torch
     import torch.distributed as dist
 
     t = torch.tensor([val], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
     return float(t.item())
+
+
+def max_over_ranks(val, dist_ctx):
+    return _reduce(val, dist_ctx, "MAX")
 
 
 def sum_over_ranks(val, dist_ctx):
-    if not dist_ctx:
-        return val
-    import torch
-    import torch.distributed as dist
-
-    t = torch.tensor([val], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+    return _reduce(val, dist_ctx, "SUM")
 
 
-def force_bytes(n_local, n_ghost, nn, half):
-    """Algorithmic bytes of one LJ force launch (SURVEY.md 8d / DESIGN.md): int32
-    indices, FP64 positions/forces, every position read once."""
+def force_bytes(n_local, n_ghost, nn, half, precision=64):
+    """Algorithmic bytes of one LJ force launch (SURVEY.md 8d / DESIGN.md): int32 indices, every
+    position read once, forces written once; FP64: 24-byte positions/forces, FP32 variant: 12."""
+    w = 24.0 if precision == 64 else 12.0
     if half:
-        return n_local * (4.0 * nn + 8.0) + (n_local + n_ghost) * (28.0 + 48.0)
-    return n_local * (4.0 * nn + 24.0 + 8.0) + (n_local + n_ghost) * (24.0 + 4.0)
+        return n_local * (4.0 * nn + 8.0) + (n_local + n_ghost) * (w + 4.0 + 2.0 * w)
+    return n_local * (4.0 * nn + w + 8.0) + (n_local + n_ghost) * (w + 4.0)
 
 
-def measure_resident(args, sim, steps, warmup, dist_ctx, sample_clocks):
-    sim.run(args.melt, 0)
+def measure_resident(args, sim, steps, warmup, dist_ctx, sample_clocks, melt=None):
+    sim.run(args.melt if melt is None else melt, 0)
     # re-anchor the rebuild cadence so every bench step holds exactly one rebuild
     sim.step = 0
     sim.run(warmup * MD_PER_STEP, args.thermo)
@@ -221,7 +240,7 @@ def measure_resident(args, sim, steps, warmup, dist_ctx, sample_clocks):
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if sample_clocks else None
     if sampler:
         sampler.start()
-    sec = timed_steps(sim, steps, args.thermo, dist_ctx)
+    sec = timed_steps(sim, steps * MD_PER_STEP, args.thermo, dist_ctx)
     clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count() - l0
     tm = ctx.timing()
@@ -232,44 +251,82 @@ def measure_resident(args, sim, steps, warmup, dist_ctx, sample_clocks):
                 nn=tot / max(nl, 1), max_neigh=mx, clocks=clocks)
 
 
+def roofline_of(m, half, precision, peak, peak_src, kernel):
+    fk_ms, fk_n = m["timing"]["force_kernel"]
+    fb = force_bytes(m["n_local"], m["n_ghost"], m["nn"], half, precision)
+    avg = fk_ms / max(fk_n, 1)
+    achieved = fb / (avg * 1e-3) / 1e9 if fk_ms > 0 else 0.0
+    return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+            "bytes_per_launch": fb, "avg_launch_ms": avg, "launches": fk_n,
+            "stored_neighbours_per_atom": m["nn"], "ghost_fraction": m["n_ghost"] / max(m["n_local"], 1),
+            "step_share": fk_ms * 1e-3 / m["sec"]}
+
+
 def measure_e2e(args, sim, steps, dist_ctx):
     """Same metric through the public C ABI with HOST buffers: every bench step uploads
-    the atoms (x, v, type, id) from pinned host memory, runs the init path + one list
-    period, and downloads x, v and the thermo scalars."""
+    this rank's atoms (x, v, type, id) from pinned host memory, runs the init path + one list
+    period, and downloads x, v, type, id (the atoms a rank owns change with migration, so the
+    whole rows come back) and the thermo scalars.  Returns seconds (max over ranks), bytes and
+    a stage breakdown (host clock with a stream sync after each stage, rank 0)."""
     import torch
 
+    from cabanamd_b200.capi import _dp, _ip
+
     ctx = sim.ctx
-    g = ctx.get_atoms(fields="xvti")
-    nl = g["n_local"]
+    nl0, _ = ctx.counts()
+    cap = nl0 + nl0 // 8 + 1024  # owned atoms drift a little between ranks
 
-    def pinned(a):
-        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
-        t.numpy()[...] = a
-        return t
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
 
-    hx, hv = pinned(g["x"][:nl]), pinned(g["v"][:nl])
-    ht, hi = pinned(g["type"][:nl]), pinned(g["id"][:nl])
+    hx, hv = pinned((cap, 3), torch.float64), pinned((cap, 3), torch.float64)
+    ht, hi = pinned((cap,), torch.int32), pinned((cap,), torch.int32)
     thermo = args.thermo
     stream = torch.cuda.ExternalStream(ctx.stream())
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
-    from cabanamd_b200.capi import _dp, _ip
+    state = {"n": 0, "h2d": 0, "d2h": 0}
+    stage = {"h2d_upload": 0.0, "init_path": 0.0, "md_steps": 0.0, "d2h_download": 0.0}
 
-    def one_step():
-        ctx.set_atoms(hx.numpy(), hv.numpy(), None, ht.numpy(), hi.numpy())
+    def download():
+        n, _ = ctx.counts()
+        assert n <= cap
+        ctx._ck(ctx.L.cbmd_get_atoms(ctx.h, 0, n, _dp(hx.numpy()), _dp(hv.numpy()), None,
+                                     _ip(ht.numpy()), _ip(hi.numpy()), None))
+        state["n"] = n
+
+    def one_step(record):
+        n = state["n"]
+        t0 = time.perf_counter()
+        ctx.set_atoms(hx.numpy()[:n], hv.numpy()[:n], None, ht.numpy()[:n], hi.numpy()[:n])
+        t1 = time.perf_counter()
         sim.setup()
+        if record:
+            ctx.sync()
+        t2 = time.perf_counter()
         sim.run(MD_PER_STEP, thermo)
-        ctx._ck(ctx.L.cbmd_get_atoms(ctx.h, 0, nl, _dp(hx.numpy()), _dp(hv.numpy()), None, None,
-                                     None, None))
+        if record:
+            ctx.sync()
+        t3 = time.perf_counter()
+        download()
+        t4 = time.perf_counter()
+        state["h2d"] += n * (24 + 24 + 4 + 4)
+        state["d2h"] += state["n"] * (24 + 24 + 4 + 4)
+        if record:
+            for k, dt in zip(stage, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                stage[k] += dt
 
-    one_step()  # warm-up
+    download()
+    one_step(False)  # warm-up
+    state["h2d"] = state["d2h"] = 0
     barrier(dist_ctx)
     ctx.sync()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(steps):
-        one_step()
+        one_step(False)
     ctx.sync()
     e1.record(stream)
     torch.cuda.synchronize()
@@ -277,21 +334,30 @@ def measure_e2e(args, sim, steps, dist_ctx):
     barrier(dist_ctx)
     sec = max(e0.elapsed_time(e1) * 1e-3, wall)
     sec = max_over_ranks(sec, dist_ctx)
-    h2d = nl * (24 + 24 + 4 + 4)
     n_thermo = (MD_PER_STEP // thermo) if thermo else 0
-    d2h = nl * 48 + n_thermo * 3 * 8
-    return sec, sum_over_ranks(h2d, dist_ctx), sum_over_ranks(d2h, dist_ctx)
+    h2d = state["h2d"] / steps
+    d2h = state["d2h"] / steps + n_thermo * 3 * 8
+    one_step(True)  # untimed: stage breakdown
+    barrier(dist_ctx)
+    return sec, sum_over_ranks(h2d, dist_ctx), sum_over_ranks(d2h, dist_ctx), \
+        {k: v * 1e3 for k, v in stage.items()}
 
 
-def cpu_baseline(cells, md_steps, threads=None, half=False):
+def oracle_threads():
+    """All host cores for the oracle (torchrun exports OMP_NUM_THREADS=1)."""
+    import oracle_lib as O
+
+    L = O.lib()
+    L.orc_set_threads(os.cpu_count() or 1)
+    return L.orc_max_threads()
+
+
+def cpu_baseline(cells, md_steps, half=False):
     """The oracle (a port of the reference algorithm: the real Kokkos/Cabana build is not
     available in this image) on the host cores; bounded sample."""
     import oracle_lib as O
 
-    L = O.lib()
-    if threads:
-        L.orc_set_threads(threads)
-    nthr = L.orc_max_threads()
+    nthr = oracle_threads()
     s = O.Sim(mass=[2.0], half=half).create_lattice_fcc(cells=(cells,) * 3).setup()
     s.run(MD_PER_STEP, 10)  # warm: first rebuild
     t0 = time.perf_counter()
@@ -304,14 +370,18 @@ def cpu_baseline(cells, md_steps, threads=None, half=False):
 
 
 def run_reference(args):
+    """CPU arm: the oracle port on all host cores (rank 0 only).  Each step = 20 MD steps of ONE
+    GPU's share of the workload (the whole N-GPU system would not finish in minutes on the
+    host); the sample shrinks further when steps+warmup is large."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle_lib as O
 
-    L = O.lib()
-    nthr = L.orc_max_threads()
-    cells = args.cpu_cells
+    nthr = oracle_threads()
+    budget = 3.0e9  # atom-steps: ~100 s at 3e7 atom-steps/s
+    cells = min(args.cells, int((budget / (MD_PER_STEP * (args.steps + args.warmup)) / 4.0) ** (1.0 / 3.0)))
+    cells = max(cells, 10)
     s = O.Sim(mass=[2.0], half=args.half).create_lattice_fcc(cells=(cells,) * 3).setup()
     for _ in range(args.warmup):
         s.run(MD_PER_STEP, args.thermo)
@@ -320,16 +390,18 @@ def run_reference(args):
         s.run(MD_PER_STEP, args.thermo)
     dt = time.perf_counter() - t0
     val = s.natoms * args.steps * MD_PER_STEP / dt
-    sample = (f"each step = {MD_PER_STEP} MD steps of a {s.natoms}-atom sample (fcc {cells}^3) of "
-              f"the workload, {nthr} OpenMP threads")
+    sample = (f"each step = {MD_PER_STEP} MD steps of a {s.natoms}-atom sample (fcc {cells}^3 = "
+              f"{'one GPU share' if cells == args.cells else 'a bounded part of one GPU share'} of the "
+              f"{args.gpus}-GPU workload), {nthr} OpenMP threads")
+    cfg = workload_config(args, args.gpus)
+    cfg["workload"] += f"; CPU arm runs a sample: {s.natoms} atoms on {nthr} host threads"
+    cfg["cpu_sample_atoms"] = s.natoms
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port",
-                         "sample": sample},
+        "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "CPU arm: oracle/ (OpenMP port of the reference algorithm); the Kokkos+Cabana+MPI "
@@ -347,9 +419,99 @@ def workload_config(args, n):
         "atoms_per_gpu": atoms, "atoms_total": atoms * n,
         "md_steps_per_bench_step": MD_PER_STEP, "thermo_every": args.thermo,
         "neighbor_list": "half" if args.half else "full",
+        "force_precision": args.precision,
         "decomposition": {1: "1x1x1", 2: "2x1x1", 4: "2x2x1", 8: "2x2x2"}.get(n, str(n)),
         "l2_policy": "working set (x,v,f + neighbour table, >1 GB at 4 M atoms) exceeds the 126 MB L2; no flush",
     }
+
+
+def fresh_uid(dist_ctx, rank):
+    """Every context group needs its own NCCL unique id."""
+    if not dist_ctx:
+        return None
+    import torch.distributed as dist
+
+    import cabanamd_b200 as cb
+
+    box = [cb.Context.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+def drift_check(args, n, rank, local, dist_ctx, cells=40, md_steps=1000):
+    """configs[3]'s 1000-step energy-drift check at a size the host can follow: the in.lj deck
+    (fcc 40^3 = 256 000 atoms, thermo every 10) on the N GPUs and on the oracle with N virtual
+    ranks.  Trajectories are chaotic, so the per-step traces are compared over the first 100
+    steps and the drift / fluctuation of the total energy over the whole run."""
+    from cabanamd_b200.capi import dims_create
+
+    a = argparse.Namespace(**vars(args))
+    a.precision, a.cutoff, a.guess = 64, 2.5, 50
+    grid = dims_create(n)
+    if any(cells % g for g in grid):
+        return None
+    sim = build_sim(a, 0, False, n, rank, fresh_uid(dist_ctx, rank), local, cells_global=(cells,) * 3)
+    sim.setup()
+    sim.record_thermo()
+    sim.run(md_steps, 10)
+    th = np.array(sim.thermo)
+    sim.ctx.close()
+    out = None
+    if rank == 0:
+        import oracle_lib as O
+
+        nthr = oracle_threads()
+        t0 = time.perf_counter()
+        ref = O.Sim(mass=[2.0]).create_lattice_fcc(cells=(cells,) * 3, nranks=n).setup()
+        ref.record_thermo()
+        ref.run(md_steps, 10)
+        to = np.array(ref.thermo())
+        eg, eo = th[:, 2] + th[:, 3], to[:, 2] + to[:, 3]
+        k = 11  # rows of steps 0..100
+        out = {"deck": f"in.lj (fcc {cells}^3 = {4 * cells ** 3} atoms, {md_steps} steps, thermo/10), "
+                       f"{n} GPU rank(s) vs oracle with {n} virtual rank(s)",
+               "thermo_maxdiff_first_100_steps": float(np.abs(th[:k, 1:] - to[:k, 1:]).max()),
+               "etot_drift_gpu": float(eg[-1] - eg[0]), "etot_drift_oracle": float(eo[-1] - eo[0]),
+               "etot_maxdev_gpu": float(np.abs(eg - eg[0]).max()), "etot_maxdev_oracle": float(np.abs(eo - eo[0]).max()),
+               "etot_rms_gpu": float(np.std(eg)), "etot_rms_oracle": float(np.std(eo)),
+               "T_final_gpu": float(th[-1, 1]), "T_final_oracle": float(to[-1, 1]),
+               "oracle_seconds": time.perf_counter() - t0, "oracle_threads": nthr}
+        out["ok"] = bool(out["thermo_maxdiff_first_100_steps"] < 1e-8 and
+                         abs(out["etot_maxdev_gpu"] - out["etot_maxdev_oracle"]) < 0.5 * max(out["etot_maxdev_oracle"], 1e-6)
+                         and abs(out["T_final_gpu"] - out["T_final_oracle"]) < 0.01)
+    return out
+
+
+def strong_scaling_leg(args, n, rank, local, dist_ctx):
+    """configs[3]: 16.4 M atoms (fcc 160^3) on the N GPUs, strong scaling (total work fixed),
+    1000 MD steps with thermo every 10; reports throughput and the energy drift of that run."""
+    from cabanamd_b200.capi import dims_create
+
+    grid = dims_create(n)
+    c = args.strong_cells
+    if any(c % g for g in grid):
+        return None
+    a = argparse.Namespace(**vars(args))
+    a.precision, a.cutoff, a.guess, a.half = 64, 2.5, 50, False
+    sim = build_sim(a, 0, False, n, rank, fresh_uid(dist_ctx, rank), local, cells_global=(c,) * 3,
+                    fast_velocities=True)
+    sim.setup()
+    sim.run(100, 0)  # melt + warm
+    sim.step = 0
+    sim.thermo = []
+    sim.record_thermo()
+    sec = timed_steps(sim, args.strong_steps, 10, dist_ctx)
+    th = np.array(sim.thermo)
+    e = th[:, 2] + th[:, 3]
+    nl, ng = sim.ctx.counts()
+    res = {"value": sim.N * args.strong_steps / sec, "unit": UNIT, "scaling": "strong", "atoms_total": sim.N,
+           "atoms_per_gpu": sim.N // n, "md_steps": args.strong_steps, "ms_per_md_step": sec / args.strong_steps * 1e3,
+           "decomposition": "x".join(str(g) for g in grid), "ghost_fraction_rank0": ng / max(nl, 1),
+           "etot_drift": float(e[-1] - e[0]), "etot_maxdev": float(np.abs(e - e[0]).max()),
+           "note": "BASELINE configs[3]; velocities from a seeded numpy draw (throughput leg), melted 100 steps; "
+                   "the drift check against the oracle is extra['configs[3] drift check']"}
+    sim.ctx.close()
+    return res
 
 
 def main():
@@ -367,22 +529,28 @@ def main():
                          "for the CPU arm")
     torch.cuda.set_device(local)
     dist_ctx = None
-    uid = None
     if world > 1:
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist_ctx = True
-        import cabanamd_b200 as cb
-
-        box = [cb.Context.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        uid = box[0]
     n = world
     assert n == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    sim = build_sim(args, args.cells, args.half, n, rank, uid, local)
+    # ---- correctness first: the decomposed loop against the oracle's virtual ranks (N > 1)
+    parity = None
+    if n > 1 and not args.no_checks:
+        from mp_parity import run_parity
+
+        parity = {}
+        for half in (False, True):
+            ok, worst = run_parity(n, rank, local, fresh_uid(dist_ctx, rank), half=half, steps=45, cells=8)
+            parity["half" if half else "full"] = {"ok": bool(ok), **worst}
+        parity["what"] = (f"{n} NCCL ranks, fcc 8^3 cells/rank, 45 MD steps (2 rebuilds), thermo + per-id x/v/f + per-rank "
+                          f"ghost sets vs the oracle with {n} virtual ranks (tests/mp_parity.py)")
+
+    sim = build_sim(args, args.cells, args.half, n, rank, fresh_uid(dist_ctx, rank), local)
     sim.setup()
     m = measure_resident(args, sim, args.steps, args.warmup, dist_ctx, sample_clocks=True)
     md_steps = args.steps * MD_PER_STEP
@@ -390,7 +558,6 @@ def main():
     value = atoms_total * md_steps / m["sec"]
 
     # roofline of the dominant kernel (LJ force), measured live with CUDA events
-    fk_ms, fk_n = m["timing"]["force_kernel"]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -398,69 +565,86 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
-    fb = force_bytes(m["n_local"], m["n_ghost"], m["nn"], args.half)
-    achieved = fb / (fk_ms / max(fk_n, 1) * 1e-3) / 1e9 if fk_ms > 0 else 0.0
-    traffic = None
+    gather = int(os.environ.get("CBMD_GATHER", "1"))
+    if args.half:
+        kname = "k_force_half"
+    elif args.precision == 32:
+        kname = "k_force_full_f32 (float4 LDG.128, index stream through TEX)"
+    else:
+        kname = "k_force_full<1,...> (xy LDG.128 + z TEX)" if gather == 1 else "k_force_full<0,...> (32-byte records)"
+    roofline = roofline_of(m, args.half, args.precision, peak, peak_src, kname)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "force_traffic.json")))
-        key = f"{'half' if args.half else 'full'}_{args.cells}"
-        traffic = tr.get(key)
+        key = f"{'half' if args.half else 'full'}_{args.cells}" + ("_f32" if args.precision == 32 else "")
+        if key in tr:
+            roofline["traffic"] = tr[key]
+            roofline["traffic_source"] = tr.get("source", "ncu --set full capture, profiles/force_traffic.json (not re-measured in this run)")
     except Exception:
         pass
-    gather = int(os.environ.get("CBMD_GATHER", "1"))
-    kname = "k_force_half" if args.half else ("k_force_full<1,...> (xy LDG.128 + z TEX)" if gather == 1
-                                              else "k_force_full<0,...> (32-byte records)")
-    roofline = {"bound": "hbm", "kernel": kname,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": traffic,
-                "bytes_per_launch": fb, "avg_launch_ms": fk_ms / max(fk_n, 1), "launches": fk_n,
-                "stored_neighbours_per_atom": m["nn"], "ghost_fraction": m["n_ghost"] / m["n_local"],
-                "step_share": fk_ms * 1e-3 / m["sec"]}
+    roofline["fp64_pipe_bound_note"] = (
+        "17 FP64 instructions per stored pair at 64 FP64 lanes/clk/SM bound this sweep at ~0.31 ms per 4 M atoms "
+        "(frac 0.71); ncu sm__inst_executed_pipe_fp64 in profiles/") if args.precision == 64 and not args.half else None
     whole_step_bytes = 604.0  # SURVEY.md 8d, B/atom-step, full list
     buckets = {k: v[0] for k, v in m["timing"].items()}
 
     e2e = None
     if not args.no_e2e:
-        sec, h2d, d2h = measure_e2e(args, sim, max(1, min(args.steps, 3)), dist_ctx)
         ke = max(1, min(args.steps, 3))
+        sec, h2d, d2h, stages = measure_e2e(args, sim, ke, dist_ctx)
         e2e = {"value": atoms_total * ke * MD_PER_STEP / sec, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "note": "per bench step: pinned-host upload of x,v,type,id -> init path (wrap, sort, "
-                       "ghosts, Verlet build, force) -> 20 MD steps -> download x,v + thermo"}
+               "stage_ms_rank0": stages,
+               "note": "per bench step: pinned-host upload of x,v,type,id -> init path (wrap/migrate, sort, "
+                       "ghosts, Verlet build, force) -> 20 MD steps -> download x,v,type,id + thermo"}
 
     extra = {}
     sim.ctx.close()
     del sim
-    if n == 1 and not args.no_ab:
-        # A/B of the force kernel's gather path / sweep shape on the headline workload
-        # (DESIGN.md 3.1): 32-byte records by LDG.256 (no texture path), and 8 lanes per atom
-        for label, env in (("A/B gather=0 (32-byte records, LDG.256 only)", {"CBMD_GATHER": "0"}),):
-            os.environ.update(env)
-            try:
-                s1 = build_sim(args, args.cells, args.half, 1, 0, None, local)
-                s1.setup()
-                m1 = measure_resident(args, s1, args.steps, args.warmup, None, False)
-                f_ms, f_n = m1["timing"]["force_kernel"]
-                extra[label] = {
-                    "value": s1.N * md_steps / m1["sec"], "unit": UNIT, "atoms": s1.N,
-                    "force_kernel_ms": f_ms / max(f_n, 1),
-                    "force_bucket_ms_per_100_md_steps": m1["timing"]["force"][0] * 100.0 / md_steps}
-                s1.ctx.close()
-                del s1
-            finally:
-                for k in env:
-                    del os.environ[k]
+    md = lambda mm, st: st * MD_PER_STEP / mm["sec"]
+    if n == 1 and not args.no_ab and not args.half and args.precision == 64:
+        # A/B of the force kernel's gather path on the headline workload
+        os.environ["CBMD_GATHER"] = "0"
+        try:
+            s1 = build_sim(args, args.cells, args.half, 1, 0, None, local)
+            s1.setup()
+            m1 = measure_resident(args, s1, args.steps, args.warmup, None, False)
+            f_ms, f_n = m1["timing"]["force_kernel"]
+            extra["A/B gather=0 (32-byte records, LDG.256 only)"] = {
+                "value": s1.N * md(m1, args.steps), "unit": UNIT, "atoms": s1.N,
+                "force_kernel_ms": f_ms / max(f_n, 1),
+                "force_bucket_ms_per_100_md_steps": m1["timing"]["force"][0] * 100.0 / md_steps}
+            s1.ctx.close()
+            del s1
+        finally:
+            del os.environ["CBMD_GATHER"]
+    roofline_fp32 = None
+    if not args.no_extra and not args.half and args.precision == 64:
+        # the FP32 force variant (option precision=32) on the headline workload, every N
+        a3 = argparse.Namespace(**vars(args))
+        a3.precision = 32
+        s3 = build_sim(a3, args.cells, False, n, rank, fresh_uid(dist_ctx, rank), local)
+        s3.setup()
+        m3 = measure_resident(a3, s3, args.steps, args.warmup, dist_ctx, False)
+        roofline_fp32 = roofline_of(m3, False, 32, peak, peak_src,
+                                    "k_force_full_f32 (float4 LDG.128, index stream through TEX)")
+        roofline_fp32["bytes_convention"] = "SURVEY 8d with 12-byte positions/forces (24 -> 12)"
+        extra["FP32 force variant (precision=32), same workload"] = {
+            "value": s3.N * md(m3, args.steps), "unit": UNIT, "atoms": s3.N,
+            "force_kernel_ms": roofline_fp32["avg_launch_ms"], "roofline_frac": roofline_fp32["frac"]}
+        s3.ctx.close()
+        del s3
     if n == 1 and not args.no_extra:
         for half in (False, True):
             a2 = argparse.Namespace(**vars(args))
-            a2.half = half
+            a2.half, a2.precision = half, 64
             s2 = build_sim(a2, 63, half, 1, 0, None, local)
             s2.setup()
-            m2 = measure_resident(a2, s2, max(args.steps, 5), max(args.warmup, 3), None, False)
+            k2 = max(args.steps, 5)
+            m2 = measure_resident(a2, s2, k2, max(args.warmup, 3), None, False)
             f_ms, f_n = m2["timing"]["force_kernel"]
             fb2 = force_bytes(m2["n_local"], m2["n_ghost"], m2["nn"], half)
             extra[f"configs[1] 1M atoms {'half' if half else 'full'} list"] = {
-                "value": s2.N * max(args.steps, 5) * MD_PER_STEP / m2["sec"], "unit": UNIT,
+                "value": s2.N * md(m2, k2), "unit": UNIT,
                 "atoms": s2.N, "force_kernel_ms": f_ms / max(f_n, 1),
                 "force_kernel_GBps_algorithmic": fb2 / (f_ms / max(f_n, 1) * 1e-3) / 1e9,
                 "stored_neighbours_per_atom": m2["nn"],
@@ -468,31 +652,43 @@ def main():
             s2.ctx.close()
         # configs[4]: long cutoff, rc = 5.0 sigma (~526 stored neighbours per atom), 1 M atoms
         a5 = argparse.Namespace(**vars(args))
-        a5.half, a5.cutoff, a5.guess, a5.melt = False, 5.0, 600, 40
+        a5.half, a5.cutoff, a5.guess, a5.melt, a5.precision = False, 5.0, 600, 40, 64
         s5 = build_sim(a5, 63, False, 1, 0, None, local)
         s5.setup()
         m5 = measure_resident(a5, s5, 2, 1, None, False)
         f_ms, f_n = m5["timing"]["force_kernel"]
         fb5 = force_bytes(m5["n_local"], m5["n_ghost"], m5["nn"], False)
         extra["configs[4] 1M atoms rc=5.0 full list"] = {
-            "value": s5.N * 2 * MD_PER_STEP / m5["sec"], "unit": UNIT, "atoms": s5.N,
+            "value": s5.N * md(m5, 2), "unit": UNIT, "atoms": s5.N,
             "force_kernel_ms": f_ms / max(f_n, 1),
             "force_kernel_GBps_algorithmic": fb5 / (f_ms / max(f_n, 1) * 1e-3) / 1e9,
+            "force_kernel_frac_of_peak": fb5 / (f_ms / max(f_n, 1) * 1e-3) / 1e9 / peak,
             "stored_neighbours_per_atom": m5["nn"], "ghost_fraction": m5["n_ghost"] / m5["n_local"]}
         s5.ctx.close()
+    if not args.no_extra:
+        # configs[3]: 16.4 M atoms strong scaling on the N GPUs + the drift check vs the oracle
+        ss = strong_scaling_leg(args, n, rank, local, dist_ctx)
+        if ss:
+            extra["configs[3] 16M atoms strong scaling, 1000 steps"] = ss
+    if not args.no_checks:
+        dc = drift_check(args, n, rank, local, dist_ctx)
+        if dc:
+            extra["configs[3] drift check"] = dc
 
     cpu = None
     if rank == 0 and n == 1 and not args.no_cpu:
-        cpu = cpu_baseline(args.cpu_cells, 2 * MD_PER_STEP)
+        cpu = cpu_baseline(args.cpu_cells, 5 * MD_PER_STEP)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": m["sec"] / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.precision == 64 else "f32",
             "data": "synthetic", "config": workload_config(args, n),
             "clocks": m["clocks"], "e2e": e2e, "gpu_launches": int(m["launches"]),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_fp32": roofline_fp32, "cpu_baseline": cpu,
+            "parity_vs_oracle": parity,
             "whole_step": {"algorithmic_bytes_per_atom_step": whole_step_bytes,
                            "achieved_GBps_per_gpu": whole_step_bytes * value / n / 1e9,
                            "frac_of_peak": whole_step_bytes * value / n / 1e9 / peak},

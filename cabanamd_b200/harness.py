@@ -31,7 +31,8 @@ class Simulation:
 
     def __init__(self, ctx=None, device=0, mass=(2.0,), cut=2.5, skin=0.3, half=False,
                  exchange_rate=20, ghost_cutoff=20.0, dt=0.005, mvv2e=1.0, boltz=1.0,
-                 max_neigh_guess=50, layout=0, nranks=1, rank=0, uid=None, eps=1.0, sigma=1.0):
+                 max_neigh_guess=50, layout=0, nranks=1, rank=0, uid=None, eps=1.0, sigma=1.0,
+                 precision=64):
         self.ctx = ctx or Context(device)
         self.half, self.cut, self.skin = half, cut, skin
         self.rn = cut + skin
@@ -46,6 +47,8 @@ class Simulation:
         c.set_mass(self.mass)
         c.set_lj(*lj_tables(len(self.mass), eps, sigma, cut))
         c.comm_init(nranks, rank, uid)
+        if precision != 64:
+            c.set_option("precision", precision)  # FP32 force sweep (full lists)
         self.step = 0
         self.N = 0
         self.thermo = []
