@@ -59,11 +59,44 @@ __global__ void __launch_bounds__( 256 )
     cell_atoms[slot] = first + i;
 }
 
+// Small cells (the half-size cells of the neighbour build hold 2-3 atoms): one LANE per cell,
+// insertion sort in place; cells with more than CELL_SORT_SMALL atoms are left to k_cell_sort.
+#define CELL_SORT_SMALL 6
+__global__ void __launch_bounds__( 256 )
+    k_cell_sort_small( const int *__restrict__ cell_start, int ncells, int *__restrict__ cell_atoms )
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( c >= ncells )
+        return;
+    const int b = cell_start[c], n = cell_start[c + 1] - b;
+    if ( n <= 1 || n > CELL_SORT_SMALL )
+        return;
+    int v[CELL_SORT_SMALL];
+#pragma unroll
+    for ( int k = 0; k < CELL_SORT_SMALL; k++ )
+        v[k] = k < n ? cell_atoms[b + k] : 0x7fffffff;
+    // sorting network by repeated compare-exchange (odd-even transposition, registers only)
+#pragma unroll
+    for ( int pass = 0; pass < CELL_SORT_SMALL; pass++ )
+#pragma unroll
+        for ( int k = pass & 1; k + 1 < CELL_SORT_SMALL; k += 2 )
+        {
+            const int lo = min( v[k], v[k + 1] ), hi = max( v[k], v[k + 1] );
+            v[k] = lo;
+            v[k + 1] = hi;
+        }
+#pragma unroll
+    for ( int k = 0; k < CELL_SORT_SMALL; k++ )
+        if ( k < n )
+            cell_atoms[b + k] = v[k];
+}
+
 // one warp per cell: rank each entry by the number of smaller entries (indices are
-// unique), then rewrite the slice in ascending order.
+// unique), then rewrite the slice in ascending order.  small_done: cells of at most
+// CELL_SORT_SMALL atoms were already ordered by k_cell_sort_small.
 #define CELL_SORT_K 8
 __global__ void __launch_bounds__( 256 )
-    k_cell_sort( const int *__restrict__ cell_start, int ncells, int *__restrict__ cell_atoms )
+    k_cell_sort( const int *__restrict__ cell_start, int ncells, int *__restrict__ cell_atoms, int small_done )
 {
     const int warp = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
     const int lane = threadIdx.x & 31;
@@ -71,7 +104,7 @@ __global__ void __launch_bounds__( 256 )
         return;
     const int b = cell_start[warp], e = cell_start[warp + 1];
     const int n = e - b;
-    if ( n <= 1 )
+    if ( n <= ( small_done ? CELL_SORT_SMALL : 1 ) )
         return;
     if ( n <= 32 )
     {
@@ -156,7 +189,14 @@ void cbmd_build_cell_lists_grid( cbmd_ctx *ctx, const GridDesc &g, int first, in
         k_cell_fill<<<div_up( count, 256 ), 256, 0, s>>>( ctx->atom_cell, first, count,
                                                           ctx->cell_cursor, ctx->cell_atoms );
         CBMD_LAUNCH_CHECK( ctx );
-        k_cell_sort<<<div_up( ncells, 8 ), 256, 0, s>>>( ctx->cell_start, ncells, ctx->cell_atoms );
+        // mean occupancy decides: grids of small cells get the lane-per-cell pass first
+        const int small = (double)count < 8.0 * (double)ncells ? 1 : 0;
+        if ( small )
+        {
+            k_cell_sort_small<<<div_up( ncells, 256 ), 256, 0, s>>>( ctx->cell_start, ncells, ctx->cell_atoms );
+            CBMD_LAUNCH_CHECK( ctx );
+        }
+        k_cell_sort<<<div_up( ncells, 8 ), 256, 0, s>>>( ctx->cell_start, ncells, ctx->cell_atoms, small );
         CBMD_LAUNCH_CHECK( ctx );
     }
 }

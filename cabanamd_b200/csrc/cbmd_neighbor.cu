@@ -305,6 +305,147 @@ __global__ void __launch_bounds__( NB_THREADS )
     }
 }
 
+// ---------------------------------------------------------------------------
+// k_neigh_build_walk (option "neigh_kernel" 1, the default): one THREAD per owned atom walks
+// its own stencil on a grid of HALF-size cells (cell >= r/2, 5x5x5 stencil).
+//
+// k_neigh_build shares one staged 27-cell stencil (cells >= r) between the lanes of a warp,
+// so every lane tests every candidate of the shared stencil: ~500-800 FP32 tests per atom
+// for ~78 accepted, and the kernel is bound by instruction issue (profiles/).  The volume of
+// a 5x5x5 stencil of half-size cells is 2.7 x smaller, and a thread that walks its OWN stencil
+// tests only its own ~300 candidates.  The 25 (x,y) columns of a stencil are 25 runs that are
+// contiguous in cell order; the candidates are packed once per build in that order as 16-byte
+// records {x,y,z relative to the box centre as FP32, atom index} (k_pack_candidates), so a
+// thread streams each run with LDG.128 and the 32 neighbouring atoms of a warp hit the same
+// lines in L1.  The decision is k_neigh_build's: FP32 with an explicit error bound (M = the
+// largest relative coordinate, measured while packing), exact FP64 re-evaluation of the
+// reference criterion from the 32-byte records for the few ambiguous candidates — the SET is
+// bit-identical to the oracle's.  Rows come out in ascending (half-cell, index) order.
+//
+// Measured on B200, 4 M atoms (profiles/r2_neigh_kernels.txt): 2.0 ms + 0.3 ms for the finer
+// cell lists and the packing, against 2.85 ms for k_neigh_build — half the instructions.  But
+// the force sweep that follows is 4 % SLOWER on rows in half-cell order (0.717 ms against
+// 0.687 ms on k_neigh_build's rows, which ascend in atom index because the atoms are sorted
+// by the cells it walks): 20 sweeps lose more than one build gains, so the MD loop keeps
+// k_neigh_build (option "neigh_kernel" 0, the default) and this kernel is the A/B leg.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__( 256 )
+    k_pack_candidates( const XT *__restrict__ xt, const int *__restrict__ cell_atoms, int n_total,
+                       double3 origin, float4 *__restrict__ cpos, int *__restrict__ mag_bits )
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    float mag = 0.f;
+    if ( s < n_total )
+    {
+        const int j = cell_atoms[s];
+        const XT r = ld_xt( xt + j );
+        const float4 c = make_float4( (float)( r.x - origin.x ), (float)( r.y - origin.y ),
+                                      (float)( r.z - origin.z ), __int_as_float( j ) );
+        cpos[s] = c;
+        mag = fmaxf( fabsf( c.x ), fmaxf( fabsf( c.y ), fabsf( c.z ) ) );
+    }
+    for ( int o = 16; o > 0; o >>= 1 )
+        mag = fmaxf( mag, __shfl_xor_sync( 0xffffffffu, mag, o ) );
+    if ( ( threadIdx.x & 31 ) == 0 && mag > 0.f )
+        atomicMax( mag_bits, __float_as_int( mag ) ); // non-negative floats order like ints
+}
+
+template <bool HALF>
+__global__ void __launch_bounds__( 128 )
+    k_neigh_build_walk( const XT *__restrict__ xt, int n_local, GridDesc g,
+                        const int *__restrict__ cell_start, const float4 *__restrict__ cpos,
+                        const int *__restrict__ atom_cell, double3 origin, double rsqr,
+                        const int *__restrict__ mag_bits, int *__restrict__ nb, int nb_rows,
+                        int *__restrict__ nb_count, int *__restrict__ d_max, int zr_cells )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int count = 0;
+    if ( i < n_local )
+    {
+        // FP32 error of d2: relative coordinates carry <= 2^-24*M each, so |fx - dx| <= 1.2e-7*M
+        // and, with three more roundings in the sum, |d2f - d2| <= (8.4e-7*M + 1.8e-7)*(1 + d2);
+        // tol0 is > 10x that (same bound as k_neigh_build)
+        const float M = __int_as_float( *mag_bits );
+        const float r2f = (float)rsqr;
+        const float tol0 = 4.0e-6f + 1.0e-5f * M;
+        const float r2lo = ( r2f - tol0 ) / ( 1.0f + tol0 ) * 0.999999f;
+        const float r2hi = ( r2f + tol0 ) / ( 1.0f - tol0 ) * 1.000001f;
+        const float tolx = 1.0e-5f * fmaxf( 1.0f, M );
+        const XT xi = ld_xt( xt + i );
+        const float xr = (float)( xi.x - origin.x ), yr = (float)( xi.y - origin.y ), zr = (float)( xi.z - origin.z );
+        const int c = atom_cell[i];
+        const int nz = g.n[2], ny = g.n[1], nx = g.n[0];
+        const int cz = c % nz, cy = ( c / nz ) % ny, cx = c / ( nz * ny );
+        const int zlo = max( cz - zr_cells, 0 ), zhi = min( cz + zr_cells, nz - 1 );
+        const int alo = max( cx - 2, 0 ), ahi = min( cx + 2, nx - 1 );
+        const int blo = max( cy - 2, 0 ), bhi = min( cy + 2, ny - 1 );
+        char *const row0 = (char *)( nb + nb_tile_base( i, nb_rows ) );
+        for ( int a = alo; a <= ahi; a++ )
+            for ( int b = blo; b <= bhi; b++ )
+            {
+                const int row = ( a * ny + b ) * nz;
+                const int s0 = __ldg( cell_start + row + zlo ), s1 = __ldg( cell_start + row + zhi + 1 );
+                // the run in chunks of 32 candidates: first DECIDE (one bit per candidate, a short
+                // loop without stores), then APPEND the accepted ones (~1 in 4) — the address
+                // arithmetic of an append is not paid for the rejected candidates
+                for ( int c0 = s0; c0 < s1; c0 += 32 )
+                {
+                    const int c1 = min( c0 + 32, s1 );
+                    unsigned sure = 0u, amb = 0u;
+#pragma unroll 4
+                    for ( int s = c0; s < c1; s++ )
+                    {
+                        const float4 q = __ldg( cpos + s );
+                        const float fx = q.x - xr, fy = q.y - yr, fz = q.z - zr;
+                        const float d2 = fx * fx + fy * fy + fz * fz;
+                        bool in_lo = d2 < r2lo, in_hi = d2 < r2hi;
+                        if ( HALF )
+                        { // xj > xi decided in FP32 unless |xj - xi| is within its error
+                            in_lo = in_lo && fx > tolx;
+                            in_hi = in_hi && fx >= -tolx;
+                        }
+                        const unsigned bit = 1u << ( s - c0 );
+                        sure |= in_lo ? bit : 0u;
+                        amb |= in_hi ? bit : 0u;
+                    }
+                    amb &= ~sure;
+                    while ( amb )
+                    { // exact re-evaluation of the reference criterion (rare)
+                        const int k = __ffs( amb ) - 1;
+                        amb &= amb - 1u;
+                        const int j = __float_as_int( __ldg( cpos + c0 + k ).w );
+                        const XT xj = ld_xt( xt + j );
+                        bool ok = dist2_exact( __dsub_rn( xi.x, xj.x ), __dsub_rn( xi.y, xj.y ), __dsub_rn( xi.z, xj.z ) ) <= rsqr;
+                        if ( HALF )
+                            ok = ok && half_valid( xi, xj );
+                        sure |= ok ? ( 1u << k ) : 0u;
+                    }
+                    while ( sure )
+                    {
+                        const int k = __ffs( sure ) - 1;
+                        sure &= sure - 1u;
+                        const int j = __float_as_int( __ldg( &cpos[c0 + k].w ) );
+                        if ( j != i ) // the atom itself passes the distance test
+                        {
+                            if ( count < nb_rows )
+                                *(int *)( row0 + ( ( (unsigned)count >> 2 ) << 9 ) + ( ( (unsigned)count & 3u ) << 2 ) ) = j;
+                            count++;
+                        }
+                    }
+                }
+            }
+        nb_count[i] = count;
+        // pad the row to a multiple of four with the atom itself (never a neighbour)
+        for ( int k = count; k < min( ( count + 3 ) & ~3, nb_rows ); k++ )
+            *(int *)( row0 + ( ( (unsigned)k >> 2 ) << 9 ) + ( ( (unsigned)k & 3u ) << 2 ) ) = i;
+    }
+    int mx = count;
+    for ( int o = 16; o > 0; o >>= 1 )
+        mx = max( mx, __shfl_xor_sync( 0xffffffffu, mx, o ) );
+    if ( ( threadIdx.x & 31 ) == 0 && mx > 0 )
+        atomicMax( d_max, mx );
+}
+
 __global__ void __launch_bounds__( 256 )
     k_nb_to_csr( const int *__restrict__ nb, int nb_rows,
                  const int *__restrict__ nb_count, const int64_t *__restrict__ offsets, int n_local,
@@ -418,15 +559,19 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
 
     // cell grid of size >= rcut around the owned box; atoms outside are clamped into
     // the edge cells, which keeps |cell(i)-cell(j)| <= 1 for every pair within rcut.
-    const double din[3] = { rcut, rcut, rcut };
+    // option "neigh_kernel" 0 (default): cells >= rcut, one halo layer, staged 27-cell stencil;
+    // 1: cells >= rcut/2, two halo layers, 5x5x5 stencil walked by one thread per atom
+    const bool walk = ctx->neigh_kernel == 1;
+    const double cell = walk ? 0.5 * rcut : rcut;
+    const double din[3] = { cell, cell, cell };
     int nbin[3];
     double gmin[3], gmax[3];
     GridDesc g;
-    cbmd_binning_grid( ctx, din, 1, nbin, gmin, gmax, g );
+    cbmd_binning_grid( ctx, din, walk ? 2 : 1, nbin, gmin, gmax, g );
     for ( int d = 0; d < 3; d++ )
-        if ( 1.0 / g.rdx[d] < rcut )
+        if ( 1.0 / g.rdx[d] < din[d] )
         {
-            // owned box thinner than the cutoff: one cell spans this dimension
+            // owned box thinner than the cell: one cell spans this dimension
             g.n[d] = 1;
             g.rdx[d] = 0.0;
         }
@@ -444,8 +589,28 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
                                          0.5 * ( ctx->llo[1] + ctx->lhi[1] ),
                                          0.5 * ( ctx->llo[2] + ctx->lhi[2] ) );
     int *d_max = ctx->d_flags;
+    int *d_mag = ctx->d_flags + 9;
     if ( n_total > 0 )
         CBMD_CUDA( cudaMemsetAsync( ctx->nb_count, 0, (size_t)n_total * sizeof( int ), s ) );
+    if ( walk && n_total > 0 )
+    {
+        // candidates packed in cell order: {x,y,z relative to the box centre as FP32, index}
+        if ( ctx->cpos_cap < ctx->cap )
+        {
+            if ( ctx->cpos )
+            {
+                CBMD_CUDA( cudaStreamSynchronize( s ) );
+                CBMD_CUDA( cudaFree( ctx->cpos ) );
+            }
+            ctx->cpos = nullptr;
+            CBMD_CUDA( cudaMalloc( &ctx->cpos, (size_t)ctx->cap * sizeof( float4 ) ) );
+            ctx->cpos_cap = ctx->cap;
+        }
+        CBMD_CUDA( cudaMemsetAsync( d_mag, 0, sizeof( int ), s ) );
+        k_pack_candidates<<<div_up( n_total, 256 ), 256, 0, s>>>( ctx->xt, ctx->cell_atoms, n_total, centre,
+                                                                  ctx->cpos, d_mag );
+        CBMD_LAUNCH_CHECK( ctx );
+    }
     int observed = 0;
     for ( int attempt = 0; attempt < 3; attempt++ )
     {
@@ -480,7 +645,19 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
         ctx->nb_rows = rows;
         ctx->nb_stride = stride;
         CBMD_CUDA( cudaMemsetAsync( d_max, 0, sizeof( int ), s ) );
-        if ( n_local > 0 )
+        if ( n_local > 0 && walk )
+        {
+            if ( half )
+                k_neigh_build_walk<true><<<div_up( n_local, 128 ), 128, 0, s>>>(
+                    ctx->xt, n_local, g, ctx->cell_start, ctx->cpos, ctx->atom_cell, centre, rsqr, d_mag, ctx->nb,
+                    rows, ctx->nb_count, d_max, 2 );
+            else
+                k_neigh_build_walk<false><<<div_up( n_local, 128 ), 128, 0, s>>>(
+                    ctx->xt, n_local, g, ctx->cell_start, ctx->cpos, ctx->atom_cell, centre, rsqr, d_mag, ctx->nb,
+                    rows, ctx->nb_count, d_max, 2 );
+            CBMD_LAUNCH_CHECK( ctx );
+        }
+        else if ( n_local > 0 )
         {
             const int blocks = g.n[0] * g.n[1] * ( ( g.n[2] + NBC - 1 ) / NBC );
 #define NB_LAUNCH( H )                                                                            \

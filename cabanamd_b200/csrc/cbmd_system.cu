@@ -225,6 +225,8 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
             ctx->overlap = atoi( e );
         if ( const char *e = getenv( "CBMD_GATHER" ) ) // A/B switch: 0 = 32-byte records by LDG.256
             ctx->gather_mode = atoi( e ) == 0 ? 0 : 1;
+        if ( const char *e = getenv( "CBMD_NEIGH_KERNEL" ) ) // A/B switch: 1 = per-thread walk, half-size cells
+            ctx->neigh_kernel = atoi( e ) == 1 ? 1 : 0;
         if ( const char *e = getenv( "CBMD_PRECISION" ) ) // 32 = FP32 pair arithmetic (full lists)
             ctx->precision = atoi( e ) == 32 ? 32 : 64;
         CBMD_CUDA( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
@@ -289,7 +291,7 @@ extern "C" int cbmd_destroy( cbmd_ctx *ctx )
                      ctx->cell_atoms, ctx->atom_cell,   ctx->perm,       ctx->nb,
                      ctx->nb_count,   ctx->ghost_owner, ctx->ghost_image, ctx->sendbuf,
                      ctx->recvbuf,    ctx->scratch,     ctx->d_red,      ctx->d_flags,
-                     ctx->pe_partial, ctx->tile_list, ctx->tile_flag, ctx->scan_tmp };
+                     ctx->pe_partial, ctx->tile_list, ctx->tile_flag, ctx->scan_tmp, ctx->cpos };
     for ( void *p : ptrs )
         if ( p )
             cudaFree( p );
@@ -333,6 +335,14 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
         if ( (int)value != 0 && (int)value != 1 )
             throw CbmdError( "gather must be 0 (32-byte records by LDG.256) or 1 (mirror: xy LDG.128 + z TEX, FP32 float4)" );
         ctx->gather_mode = (int)value;
+    }
+    else if ( n == "neigh_kernel" )
+    {
+        // Verlet build: 0 = warp per cell over a staged 27-cell stencil (default); 1 = one thread
+        // per atom walks a 5x5x5 stencil of half-size cells.  Same sets, bit for bit.
+        if ( (int)value != 0 && (int)value != 1 )
+            throw CbmdError( "neigh_kernel must be 0 or 1" );
+        ctx->neigh_kernel = (int)value;
     }
     else if ( n == "precision" )
     {
