@@ -71,43 +71,53 @@ __global__ void __launch_bounds__( 256 )
     }
 }
 
-// Selects the atoms of [0,n) passing the face test and, when the phase has a remote peer,
-// swaps the send count with it — the count travels device to device (no host staging) and
-// both numbers come back in ONE read-back, so a phase costs a single host synchronisation.
-// pos (device, n+1 ints) holds the exclusive scan of the flags.
-static void select_face( cbmd_ctx *ctx, int n, int d, int mode, double thr, bool remote,
-                         int peer_send, int peer_recv, int **pos_out, int *n_send, int *n_recv )
+// Both faces of one dimension at once.  The two phases of a dimension never feed each other
+// (the odd phase skips what the even phase has just received, comm_mpi_impl.h:301-303; an atom
+// that arrived through the low face cannot leave through it), so their selections run on the
+// same state and ONE count swap (one NCCL group) + ONE host synchronisation serve both —
+// half the blocking round trips of a rebuild step.  pos[k] (device, n+1 ints) holds the
+// exclusive scan of phase k's flags.
+static void select_pair( cbmd_ctx *ctx, int n, int d, const int mode[2], const double thr[2], bool remote,
+                         const int peer_send[2], const int peer_recv[2], int *pos[2], int n_send[2],
+                         int n_recv[2] )
 {
     cudaStream_t s = ctx->stream;
-    int *pos = nullptr;
-    const int *d_count = nullptr;
+    int *d_cnt = ctx->d_flags + 24, *d_in = ctx->d_flags + 26;
+    pos[0] = pos[1] = nullptr;
     if ( n > 0 )
     {
-        pos = (int *)cbmd_scratch( ctx, (size_t)( n + 1 ) * sizeof( int ) );
-        k_face_flags<<<div_up( n + 1, 256 ), 256, 0, s>>>( ctx->xt, n, d, mode, thr, pos );
-        CBMD_LAUNCH_CHECK( ctx );
-        cbmd_exclusive_scan_int( ctx, pos, n );
-        d_count = pos + n;
+        const size_t pb = ( (size_t)( n + 1 ) * sizeof( int ) + 255 ) & ~(size_t)255;
+        char *st = (char *)cbmd_scratch( ctx, 2 * pb );
+        for ( int k = 0; k < 2; k++ )
+        {
+            pos[k] = (int *)( st + k * pb );
+            k_face_flags<<<div_up( n + 1, 256 ), 256, 0, s>>>( ctx->xt, n, d, mode[k], thr[k], pos[k] );
+            CBMD_LAUNCH_CHECK( ctx );
+            cbmd_exclusive_scan_int( ctx, pos[k], n );
+            CBMD_CUDA( cudaMemcpyAsync( d_cnt + k, pos[k] + n, sizeof( int ), cudaMemcpyDeviceToDevice, s ) );
+        }
     }
     else
-    {
-        CBMD_CUDA( cudaMemsetAsync( ctx->d_flags + 18, 0, sizeof( int ), s ) );
-        d_count = ctx->d_flags + 18;
-    }
-    CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i, d_count, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
+        CBMD_CUDA( cudaMemsetAsync( d_cnt, 0, 2 * sizeof( int ), s ) );
+    CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i + 8, d_cnt, 2 * sizeof( int ), cudaMemcpyDeviceToHost, s ) );
     if ( remote )
     {
-        int *d_in = ctx->d_flags + 17;
+        // with two ranks in this dimension both messages go to the same peer: sends and
+        // receives are issued in phase order on both sides, which is how NCCL pairs them
         CBMD_NCCL( ncclGroupStart() );
-        CBMD_NCCL( ncclSend( d_count, 1, ncclInt, peer_send, ctx->nccl, s ) );
-        CBMD_NCCL( ncclRecv( d_in, 1, ncclInt, peer_recv, ctx->nccl, s ) );
+        for ( int k = 0; k < 2; k++ )
+            CBMD_NCCL( ncclSend( d_cnt + k, 1, ncclInt, peer_send[k], ctx->nccl, s ) );
+        for ( int k = 0; k < 2; k++ )
+            CBMD_NCCL( ncclRecv( d_in + k, 1, ncclInt, peer_recv[k], ctx->nccl, s ) );
         CBMD_NCCL( ncclGroupEnd() );
-        CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i + 1, d_in, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
+        CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i + 10, d_in, 2 * sizeof( int ), cudaMemcpyDeviceToHost, s ) );
     }
     CBMD_CUDA( cudaStreamSynchronize( s ) );
-    *pos_out = pos;
-    *n_send = ctx->h_pinned_i[0];
-    *n_recv = remote ? ctx->h_pinned_i[1] : ctx->h_pinned_i[0];
+    for ( int k = 0; k < 2; k++ )
+    {
+        n_send[k] = ctx->h_pinned_i[8 + k];
+        n_recv[k] = remote ? ctx->h_pinned_i[10 + k] : n_send[k];
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -176,23 +186,25 @@ struct alignas( 8 ) MigTuple
     double q;
 };
 
-// stable partition: stayers keep their order in the alt arrays, leavers are packed
-// (with the PBC shift applied on the edge rank, comm_mpi.h:171-237)
+// both faces of one dimension: stayers keep their order, leavers through the high / low face
+// are packed into their own send segments (PBC shift applied on the edge ranks)
 __global__ void __launch_bounds__( 256 )
-    k_migrate_split( const XT *__restrict__ xt, const double *__restrict__ v,
-                     const double *__restrict__ f, const int *__restrict__ id,
-                     const double *__restrict__ q, int cap, int n, int d, int mode, double thr,
-                     double shift, const int *__restrict__ pos, XT *__restrict__ xt_o,
-                     double *__restrict__ v_o, double *__restrict__ f_o, int *__restrict__ id_o,
-                     double *__restrict__ q_o, MigTuple *__restrict__ out )
+    k_migrate_split2( const XT *__restrict__ xt, const double *__restrict__ v, const double *__restrict__ f,
+                      const int *__restrict__ id, const double *__restrict__ q, int cap, int n, int d,
+                      double thr_hi, double thr_lo, double shift_hi, double shift_lo,
+                      const int *__restrict__ pos_hi, const int *__restrict__ pos_lo, XT *__restrict__ xt_o,
+                      double *__restrict__ v_o, double *__restrict__ f_o, int *__restrict__ id_o,
+                      double *__restrict__ q_o, MigTuple *__restrict__ out_hi, MigTuple *__restrict__ out_lo )
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if ( i >= n )
         return;
     XT r = xt[i];
-    const int p = pos[i];
-    if ( face_test( r, d, mode, thr ) )
+    const double c = d == 0 ? r.x : ( d == 1 ? r.y : r.z );
+    const bool hi = c > thr_hi, lo = c < thr_lo; // comm_mpi.h:173,185,...: strict tests
+    if ( hi || lo )
     {
+        const double shift = hi ? shift_hi : shift_lo;
         if ( d == 0 )
             r.x += shift;
         else if ( d == 1 )
@@ -203,24 +215,27 @@ __global__ void __launch_bounds__( 256 )
         t.x[0] = r.x;
         t.x[1] = r.y;
         t.x[2] = r.z;
-        for ( int c = 0; c < 3; c++ )
+        for ( int k = 0; k < 3; k++ )
         {
-            t.v[c] = v[(size_t)c * cap + i];
-            t.f[c] = f[(size_t)c * cap + i];
+            t.v[k] = v[(size_t)k * cap + i];
+            t.f[k] = f[(size_t)k * cap + i];
         }
         t.type = (int)r.t;
         t.id = id[i];
         t.q = q[i];
-        out[p] = t;
+        if ( hi )
+            out_hi[pos_hi[i]] = t;
+        else
+            out_lo[pos_lo[i]] = t;
     }
     else
     {
-        const int o = i - p;
+        const int o = i - pos_hi[i] - pos_lo[i];
         xt_o[o] = r;
-        for ( int c = 0; c < 3; c++ )
+        for ( int k = 0; k < 3; k++ )
         {
-            v_o[(size_t)c * cap + o] = v[(size_t)c * cap + i];
-            f_o[(size_t)c * cap + o] = f[(size_t)c * cap + i];
+            v_o[(size_t)k * cap + o] = v[(size_t)k * cap + i];
+            f_o[(size_t)k * cap + o] = f[(size_t)k * cap + i];
         }
         id_o[o] = id[i];
         q_o[o] = q[i];
@@ -299,34 +314,33 @@ extern "C" int cbmd_exchange( cbmd_ctx *ctx, int *n_sent_global )
         CBMD_LAUNCH_CHECK( ctx );
     }
     int total_sent = 0;
-    for ( int ph = 0; ph < 6 && ctx->nranks > 1; ph++ )
+    for ( int d = 0; d < 3 && ctx->nranks > 1; d++ )
     {
-        const int d = ph / 2;
         if ( ctx->grid[d] <= 1 )
             continue;
-        int peer_send, peer_recv;
-        phase_peers( ctx, ph, peer_send, peer_recv );
+        // the +d and -d phases of the reference (comm_mpi_impl.h:200-262) in one step
+        int peer_send[2], peer_recv[2];
+        for ( int k = 0; k < 2; k++ )
+            phase_peers( ctx, 2 * d + k, peer_send[k], peer_recv[k] );
         // strict tests (comm_mpi.h:173,185,...): x > local_hi (even) / x < local_lo (odd)
-        const int mode = ( ph % 2 == 0 ) ? 2 : 3;
-        const double thr = ( ph % 2 == 0 ) ? ctx->lhi[d] : ctx->llo[d];
-        double shift = 0.0;
-        if ( ph % 2 == 0 && ctx->pos[d] == ctx->grid[d] - 1 )
-            shift = -ctx->gext[d];
-        if ( ph % 2 == 1 && ctx->pos[d] == 0 )
-            shift = ctx->gext[d];
+        const int mode[2] = { 2, 3 };
+        const double thr[2] = { ctx->lhi[d], ctx->llo[d] };
+        const double shift_hi = ctx->pos[d] == ctx->grid[d] - 1 ? -ctx->gext[d] : 0.0;
+        const double shift_lo = ctx->pos[d] == 0 ? ctx->gext[d] : 0.0;
         n = ctx->n_local;
-        int *pos = nullptr;
-        int n_send = 0, n_recv = 0;
-        select_face( ctx, n, d, mode, thr, true, peer_send, peer_recv, &pos, &n_send, &n_recv );
-        ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, (size_t)( n_send + 1 ) * sizeof( MigTuple ), s );
-        ensure_buf( ctx->recvbuf, ctx->recvbuf_bytes, (size_t)( n_recv + 1 ) * sizeof( MigTuple ), s );
-        if ( n_send > 0 )
+        int *pos[2];
+        int n_send[2], n_recv[2];
+        select_pair( ctx, n, d, mode, thr, true, peer_send, peer_recv, pos, n_send, n_recv );
+        const int ns = n_send[0] + n_send[1], nr = n_recv[0] + n_recv[1];
+        ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, (size_t)( ns + 1 ) * sizeof( MigTuple ), s );
+        ensure_buf( ctx->recvbuf, ctx->recvbuf_bytes, (size_t)( nr + 1 ) * sizeof( MigTuple ), s );
+        MigTuple *sb = (MigTuple *)ctx->sendbuf, *rb = (MigTuple *)ctx->recvbuf;
+        if ( ns > 0 )
         {
             // pos lives in scratch: ensure_capacity below must not run before the split
-            k_migrate_split<<<div_up( n, 256 ), 256, 0, s>>>(
-                ctx->xt, ctx->v, ctx->f, ctx->id, ctx->q, ctx->cap, n, d, mode, thr, shift, pos,
-                ctx->xt_alt, ctx->v_alt, ctx->f_alt, ctx->id_alt, ctx->q_alt,
-                (MigTuple *)ctx->sendbuf );
+            k_migrate_split2<<<div_up( n, 256 ), 256, 0, s>>>(
+                ctx->xt, ctx->v, ctx->f, ctx->id, ctx->q, ctx->cap, n, d, thr[0], thr[1], shift_hi, shift_lo,
+                pos[0], pos[1], ctx->xt_alt, ctx->v_alt, ctx->f_alt, ctx->id_alt, ctx->q_alt, sb, sb + n_send[0] );
             CBMD_LAUNCH_CHECK( ctx );
             std::swap( ctx->xt, ctx->xt_alt );
             std::swap( ctx->v, ctx->v_alt );
@@ -335,25 +349,30 @@ extern "C" int cbmd_exchange( cbmd_ctx *ctx, int *n_sent_global )
             std::swap( ctx->q, ctx->q_alt );
         }
         CBMD_NCCL( ncclGroupStart() );
-        if ( n_send > 0 )
-            CBMD_NCCL( ncclSend( ctx->sendbuf, (size_t)n_send * sizeof( MigTuple ), ncclChar,
-                                 peer_send, ctx->nccl, s ) );
-        if ( n_recv > 0 )
-            CBMD_NCCL( ncclRecv( ctx->recvbuf, (size_t)n_recv * sizeof( MigTuple ), ncclChar,
-                                 peer_recv, ctx->nccl, s ) );
+        if ( n_send[0] > 0 )
+            CBMD_NCCL( ncclSend( sb, (size_t)n_send[0] * sizeof( MigTuple ), ncclChar, peer_send[0], ctx->nccl, s ) );
+        if ( n_send[1] > 0 )
+            CBMD_NCCL( ncclSend( sb + n_send[0], (size_t)n_send[1] * sizeof( MigTuple ), ncclChar, peer_send[1],
+                                 ctx->nccl, s ) );
+        if ( n_recv[0] > 0 )
+            CBMD_NCCL( ncclRecv( rb, (size_t)n_recv[0] * sizeof( MigTuple ), ncclChar, peer_recv[0], ctx->nccl, s ) );
+        if ( n_recv[1] > 0 )
+            CBMD_NCCL( ncclRecv( rb + n_recv[0], (size_t)n_recv[1] * sizeof( MigTuple ), ncclChar, peer_recv[1],
+                                 ctx->nccl, s ) );
         CBMD_NCCL( ncclGroupEnd() );
-        const int n_keep = n - n_send;
+        const int n_keep = n - ns;
         ctx->n_local = n_keep; // so a regrow copies only live rows
-        cbmd_ensure_capacity( ctx, n_keep + n_recv );
-        if ( n_recv > 0 )
+        cbmd_ensure_capacity( ctx, n_keep + nr );
+        if ( nr > 0 )
         {
-            k_migrate_unpack<<<div_up( n_recv, 256 ), 256, 0, s>>>(
-                (const MigTuple *)ctx->recvbuf, n_recv, n_keep, ctx->cap, ctx->xt, ctx->v, ctx->f,
-                ctx->id, ctx->q );
+            // arrivals of the even phase first, then of the odd phase: the order the two
+            // sequential phases of the reference produce
+            k_migrate_unpack<<<div_up( nr, 256 ), 256, 0, s>>>( rb, nr, n_keep, ctx->cap, ctx->xt, ctx->v, ctx->f,
+                                                               ctx->id, ctx->q );
             CBMD_LAUNCH_CHECK( ctx );
         }
-        ctx->n_local = n_keep + n_recv;
-        total_sent += n_send;
+        ctx->n_local = n_keep + nr;
+        total_sent += ns;
     }
     if ( ctx->nranks > 1 )
         CBMD_REQUIRE( cbmd_reduce_sum_int( ctx, &total_sent, 1 ) == 0, cbmd_last_error() );
@@ -369,7 +388,8 @@ extern "C" int cbmd_exchange( cbmd_ctx *ctx, int *n_sent_global )
 __global__ void __launch_bounds__( 256 )
     k_halo_make_self( XT *__restrict__ xt, int *__restrict__ id, const int *__restrict__ send_idx,
                       int n, int first, int n_local, int d, double shift,
-                      int *__restrict__ owner, unsigned char *__restrict__ image )
+                      int *__restrict__ owner, unsigned char *__restrict__ image,
+                      int *__restrict__ grank, int my_rank )
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if ( k >= n )
@@ -377,11 +397,12 @@ __global__ void __launch_bounds__( 256 )
     const int sidx = send_idx[k];
     XT r = ld_xt( xt + sidx );
     unsigned char img = 0;
-    int own = sidx;
+    int own = sidx, rk = my_rank;
     if ( sidx >= n_local )
     {
         own = owner[sidx - n_local];
         img = image[sidx - n_local];
+        rk = grank[sidx - n_local];
     }
     if ( shift != 0.0 )
     {
@@ -398,6 +419,155 @@ __global__ void __launch_bounds__( 256 )
     id[g] = id[sidx];
     owner[g - n_local] = own;
     image[g - n_local] = img;
+    grank[g - n_local] = rk;
+}
+
+// Ghost record of a remote phase of the ghost build: position + type, id, and the ROOT of the
+// atom (rank that owns it, its index there, accumulated image) so that the per-step refresh can
+// fetch every ghost straight from its root instead of replaying the forwarding phases.
+struct alignas( 16 ) HaloRec
+{
+    double x, y, z;
+    long long t;
+    int id, root_rank, root_idx, image;
+};
+
+__global__ void __launch_bounds__( 256 )
+    k_halo_pack_rec( const XT *__restrict__ xt, const int *__restrict__ id, const int *__restrict__ owner,
+                     const int *__restrict__ grank, const unsigned char *__restrict__ image,
+                     const int *__restrict__ send_idx, int n, int n_local, int my_rank,
+                     HaloRec *__restrict__ out )
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( k >= n )
+        return;
+    const int sidx = send_idx[k];
+    const XT r = ld_xt( xt + sidx );
+    HaloRec h;
+    h.x = r.x;
+    h.y = r.y;
+    h.z = r.z;
+    h.t = r.t;
+    h.id = id[sidx];
+    h.root_rank = my_rank;
+    h.root_idx = sidx;
+    h.image = 0;
+    if ( sidx >= n_local )
+    {
+        h.root_rank = grank[sidx - n_local];
+        h.root_idx = owner[sidx - n_local];
+        h.image = image[sidx - n_local];
+    }
+    out[k] = h;
+}
+
+// receiver side: TagHaloPBC shift (comm_mpi.h:323-353) + bookkeeping of the root
+__global__ void __launch_bounds__( 256 )
+    k_halo_unpack_rec( const HaloRec *__restrict__ in, int n, int first, int n_local, int d, double shift,
+                       XT *__restrict__ xt, int *__restrict__ id, int *__restrict__ owner,
+                       int *__restrict__ grank, unsigned char *__restrict__ image )
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( k >= n )
+        return;
+    const HaloRec h = in[k];
+    XT r;
+    r.x = h.x;
+    r.y = h.y;
+    r.z = h.z;
+    r.t = h.t;
+    unsigned img = (unsigned)h.image;
+    if ( shift != 0.0 )
+    {
+        if ( d == 0 )
+            r.x += shift;
+        else if ( d == 1 )
+            r.y += shift;
+        else
+            r.z += shift;
+        img |= ( shift > 0.0 ? 1u : 2u ) << ( 2 * d );
+    }
+    const int g = first + k;
+    xt[g] = r;
+    id[g] = h.id;
+    owner[g - n_local] = h.root_idx;
+    grank[g - n_local] = h.root_rank;
+    image[g - n_local] = (unsigned char)img;
+}
+
+// ---- one-stage plan: ghosts grouped by root rank (stable), request lists for the roots
+__global__ void __launch_bounds__( 256 )
+    k_rank_flags( const int *__restrict__ grank, int n, int p, int *__restrict__ flags )
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( g < n )
+        flags[g] = grank[g] == p ? 1 : 0;
+    if ( g == n )
+        flags[n] = 0;
+}
+
+__global__ void __launch_bounds__( 256 )
+    k_rank_slots( const int *__restrict__ grank, const int *__restrict__ owner, int n, int p,
+                  const int *__restrict__ pos, int base, int *__restrict__ slot, int *__restrict__ req )
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( g >= n || grank[g] != p )
+        return;
+    slot[g] = base + pos[g];
+    req[base + pos[g]] = owner[g];
+}
+
+// per step, export side: the positions the other ranks want, three doubles per atom
+__global__ void __launch_bounds__( 256 )
+    k_halo_pack_flat( const XT *__restrict__ xt, const int *__restrict__ export_idx, int n,
+                      double *__restrict__ out )
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( k >= n )
+        return;
+    const XT r = ld_xt( xt + export_idx[k] );
+    out[3 * (size_t)k] = r.x;
+    out[3 * (size_t)k + 1] = r.y;
+    out[3 * (size_t)k + 2] = r.z;
+}
+
+// per step, import side: every ghost = its root's position (from the receive buffer, or from
+// this rank's own atoms) + the accumulated image shift; each coordinate is shifted at most
+// once, so the values are bit-identical to the forwarding scheme's
+__global__ void __launch_bounds__( 256 )
+    k_halo_unpack_flat( XT *__restrict__ xt, int n_local, int n_ghost, const int *__restrict__ owner,
+                        const int *__restrict__ grank, const unsigned char *__restrict__ image,
+                        const int *__restrict__ slot, const double *__restrict__ recv3, int my_rank,
+                        double Lx, double Ly, double Lz, const MirrorPtrs mir )
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( g >= n_ghost )
+        return;
+    XT r = xt[n_local + g]; // keeps the type
+    if ( grank[g] == my_rank )
+    {
+        const XT o = ld_xt( xt + owner[g] );
+        r.x = o.x;
+        r.y = o.y;
+        r.z = o.z;
+    }
+    else
+    {
+        const size_t k = 3 * (size_t)slot[g];
+        r.x = recv3[k];
+        r.y = recv3[k + 1];
+        r.z = recv3[k + 2];
+    }
+    const unsigned img = image[g];
+    const unsigned ix = img & 3u, iy = ( img >> 2 ) & 3u, iz = ( img >> 4 ) & 3u;
+    if ( ix )
+        r.x += ( ix == 1u ? Lx : -Lx );
+    if ( iy )
+        r.y += ( iy == 1u ? Ly : -Ly );
+    if ( iz )
+        r.z += ( iz == 1u ? Lz : -Lz );
+    xt[n_local + g] = r;
+    mirror_store( mir, n_local + g, r );
 }
 
 __global__ void __launch_bounds__( 256 )
@@ -425,6 +595,100 @@ __global__ void __launch_bounds__( 256 )
     *c += shift;
 }
 
+// ---------------------------------------------------------------------------
+// One-stage refresh plan (multi-rank).  The reference replays its six forwarding phases
+// every step (comm_mpi_impl.h:369-408): x ghosts must have landed before the y phase can
+// forward them, y before z — three dependent exchanges.  Every ghost is an image of ONE
+// owned atom somewhere (its root, carried along while the ghost shell is built), so the
+// refresh can fetch it from the root directly: one pack kernel, ONE NCCL group with all peers
+// in flight together, one unpack kernel that also applies the accumulated shift.  The plan is
+// made once per rebuild: ghosts grouped by root rank in ghost order (stable), counts
+// exchanged with one all-gather, request lists (root indices) sent to the roots.
+// ---------------------------------------------------------------------------
+static void build_flat_plan( cbmd_ctx *ctx )
+{
+    cudaStream_t s = ctx->stream;
+    const int np = ctx->nranks, me = ctx->rank, ng = ctx->n_ghost;
+    ctx->rcnt.assign( np, 0 );
+    ctx->roff.assign( np, 0 );
+    ctx->scnt.assign( np, 0 );
+    ctx->soff.assign( np, 0 );
+    // import side: slots of the receive buffer, peer by peer; request lists in the same order
+    int *req = nullptr;
+    int *pos = nullptr;
+    if ( ng > 0 )
+    {
+        const size_t pb = ( (size_t)( ng + 1 ) * sizeof( int ) + 255 ) & ~(size_t)255;
+        char *st = (char *)cbmd_scratch( ctx, 2 * pb + (size_t)np * sizeof( int ) );
+        pos = (int *)st;
+        req = (int *)( st + pb );
+    }
+    int *d_cnt = ctx->d_flags + 32;        // my counts per root rank
+    int *d_all = ctx->d_flags + 32 + 64;   // everybody's counts [np][np]
+    CBMD_REQUIRE( np <= 64, "one-stage halo plan supports at most 64 ranks" );
+    CBMD_CUDA( cudaMemsetAsync( d_cnt, 0, (size_t)np * sizeof( int ), s ) );
+    // counts first (device to device), then the slots once the offsets are known on the host
+    for ( int p = 0; p < np && ng > 0; p++ )
+    {
+        if ( p == me )
+            continue;
+        k_rank_flags<<<div_up( ng + 1, 256 ), 256, 0, s>>>( ctx->ghost_rank, ng, p, pos );
+        CBMD_LAUNCH_CHECK( ctx );
+        cbmd_exclusive_scan_int( ctx, pos, ng );
+        CBMD_CUDA( cudaMemcpyAsync( d_cnt + p, pos + ng, sizeof( int ), cudaMemcpyDeviceToDevice, s ) );
+    }
+    CBMD_NCCL( ncclAllGather( d_cnt, d_all, np, ncclInt, ctx->nccl, s ) );
+    std::vector<int> all( (size_t)np * np );
+    CBMD_CUDA( cudaMemcpyAsync( all.data(), d_all, all.size() * sizeof( int ), cudaMemcpyDeviceToHost, s ) );
+    CBMD_CUDA( cudaStreamSynchronize( s ) );
+    int ro = 0, so = 0;
+    for ( int p = 0; p < np; p++ )
+    {
+        ctx->rcnt[p] = all[(size_t)me * np + p]; // ghosts of mine rooted on p
+        ctx->scnt[p] = all[(size_t)p * np + me]; // atoms of mine that p wants
+        ctx->roff[p] = ro;
+        ctx->soff[p] = so;
+        ro += ctx->rcnt[p];
+        so += ctx->scnt[p];
+    }
+    ctx->n_import = ro;
+    ctx->n_export = so;
+    if ( so > ctx->export_cap )
+    {
+        if ( ctx->export_idx )
+            CBMD_CUDA( cudaFree( ctx->export_idx ) );
+        ctx->export_cap = so + so / 4 + 256;
+        CBMD_CUDA( cudaMalloc( &ctx->export_idx, (size_t)ctx->export_cap * sizeof( int ) ) );
+    }
+    for ( int p = 0; p < np && ng > 0; p++ )
+    {
+        if ( p == me || ctx->rcnt[p] == 0 )
+            continue;
+        k_rank_flags<<<div_up( ng + 1, 256 ), 256, 0, s>>>( ctx->ghost_rank, ng, p, pos );
+        CBMD_LAUNCH_CHECK( ctx );
+        cbmd_exclusive_scan_int( ctx, pos, ng );
+        k_rank_slots<<<div_up( ng, 256 ), 256, 0, s>>>( ctx->ghost_rank, ctx->ghost_owner, ng, p, pos,
+                                                        ctx->roff[p], ctx->ghost_slot, req );
+        CBMD_LAUNCH_CHECK( ctx );
+    }
+    // request lists to the roots; what the others want from me comes back
+    CBMD_NCCL( ncclGroupStart() );
+    for ( int p = 0; p < np; p++ )
+    {
+        if ( p == me )
+            continue;
+        if ( ctx->rcnt[p] > 0 )
+            CBMD_NCCL( ncclSend( req + ctx->roff[p], ctx->rcnt[p], ncclInt, p, ctx->nccl, s ) );
+        if ( ctx->scnt[p] > 0 )
+            CBMD_NCCL( ncclRecv( ctx->export_idx + ctx->soff[p], ctx->scnt[p], ncclInt, p, ctx->nccl, s ) );
+    }
+    CBMD_NCCL( ncclGroupEnd() );
+    ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, 3 * (size_t)( so + 1 ) * sizeof( double ), s );
+    ensure_buf( ctx->recvbuf, ctx->recvbuf_bytes, 3 * (size_t)( ro + 1 ) * sizeof( double ), s );
+    // (req lives in scratch: later users of scratch are ordered behind the sends on this stream)
+    ctx->flat_mp_ok = true;
+}
+
 extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
 {
     CBMD_API_BEGIN
@@ -439,89 +703,100 @@ extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
     ctx->nb_n = 0;
     ctx->nb_ntot = 0;
     bool all_self = true;
-    for ( int ph = 0; ph < 6; ph++ )
+    for ( int d = 0; d < 3; d++ )
     {
-        HaloPhase &P = ctx->phase[ph];
-        const int d = ph / 2;
-        phase_peers( ctx, ph, P.peer_send, P.peer_recv );
-        const bool self = ( P.peer_send == ctx->rank );
+        // the two phases of a dimension (+d then -d, comm_mpi_impl.h:280-367) in one step: the odd
+        // phase never sends what the even phase has just received (:301-303), so both select
+        // from the same atoms and share one count swap and one host synchronisation
+        HaloPhase *P[2] = { &ctx->phase[2 * d], &ctx->phase[2 * d + 1] };
+        int peer_send[2], peer_recv[2];
+        for ( int k = 0; k < 2; k++ )
+        {
+            phase_peers( ctx, 2 * d + k, P[k]->peer_send, P[k]->peer_recv );
+            peer_send[k] = P[k]->peer_send;
+            peer_recv[k] = P[k]->peer_recv;
+        }
+        const bool self = ( peer_send[0] == ctx->rank );
         all_self = all_self && self;
-        // comm_mpi_impl.h:301-303
-        const int np = ctx->n_local + ctx->n_ghost - ( ( ph % 2 == 1 ) ? ctx->phase[ph - 1].n_recv : 0 );
+        const int np = ctx->n_local + ctx->n_ghost;
         // comm_mpi.h:249,263,...: x >= hi - depth (even) / x <= lo + depth (odd)
-        const int mode = ( ph % 2 == 0 ) ? 0 : 1;
-        const double thr = ( ph % 2 == 0 ) ? ctx->lhi[d] - comm_depth : ctx->llo[d] + comm_depth;
-        int *pos = nullptr;
-        select_face( ctx, np, d, mode, thr, !self, P.peer_send, P.peer_recv, &pos, &P.n_send, &P.n_recv );
-        if ( P.n_send > P.send_cap )
+        const int mode[2] = { 0, 1 };
+        const double thr[2] = { ctx->lhi[d] - comm_depth, ctx->llo[d] + comm_depth };
+        int *pos[2];
+        int n_send[2], n_recv[2];
+        select_pair( ctx, np, d, mode, thr, !self, peer_send, peer_recv, pos, n_send, n_recv );
+        for ( int k = 0; k < 2; k++ )
         {
-            if ( P.send_idx )
-                CBMD_CUDA( cudaFree( P.send_idx ) );
-            P.send_cap = (int)( P.n_send * 1.1 ) + 256; // comm_mpi_impl.h:313 growth policy
-            CBMD_CUDA( cudaMalloc( &P.send_idx, (size_t)P.send_cap * sizeof( int ) ) );
-        }
-        if ( P.n_send > 0 )
-        {
-            k_select_scatter<<<div_up( np, 256 ), 256, 0, s>>>( ctx->xt, np, d, mode, thr, pos,
-                                                                P.send_idx, P.send_cap );
-            CBMD_LAUNCH_CHECK( ctx );
-        }
-        // receiver-side PBC shift (TagHaloPBC)
-        P.shift = 0.0;
-        if ( ph % 2 == 0 && ctx->pos[d] == 0 )
-            P.shift = -ctx->gext[d];
-        if ( ph % 2 == 1 && ctx->pos[d] == ctx->grid[d] - 1 )
-            P.shift = ctx->gext[d];
-        const int first = ctx->n_local + ctx->n_ghost;
-        P.recv_first = first;
-        if ( self )
-        {
-            P.n_recv = P.n_send;
-            cbmd_ensure_capacity( ctx, first + P.n_recv );
-            if ( P.n_recv > 0 )
+            P[k]->n_send = n_send[k];
+            P[k]->n_recv = n_recv[k];
+            if ( n_send[k] > P[k]->send_cap )
             {
-                k_halo_make_self<<<div_up( P.n_recv, 256 ), 256, 0, s>>>(
-                    ctx->xt, ctx->id, P.send_idx, P.n_recv, first, ctx->n_local, d, P.shift,
-                    ctx->ghost_owner, ctx->ghost_image );
+                if ( P[k]->send_idx )
+                    CBMD_CUDA( cudaFree( P[k]->send_idx ) );
+                P[k]->send_cap = (int)( n_send[k] * 1.1 ) + 256; // comm_mpi_impl.h:313 growth policy
+                CBMD_CUDA( cudaMalloc( &P[k]->send_idx, (size_t)P[k]->send_cap * sizeof( int ) ) );
+            }
+            if ( n_send[k] > 0 )
+            {
+                k_select_scatter<<<div_up( np, 256 ), 256, 0, s>>>( ctx->xt, np, d, mode[k], thr[k], pos[k],
+                                                                    P[k]->send_idx, P[k]->send_cap );
                 CBMD_LAUNCH_CHECK( ctx );
             }
+        }
+        // receiver-side PBC shift (TagHaloPBC)
+        P[0]->shift = ctx->pos[d] == 0 ? -ctx->gext[d] : 0.0;
+        P[1]->shift = ctx->pos[d] == ctx->grid[d] - 1 ? ctx->gext[d] : 0.0;
+        const int first = ctx->n_local + ctx->n_ghost;
+        P[0]->recv_first = first;
+        P[1]->recv_first = first + n_recv[0];
+        const int nr = n_recv[0] + n_recv[1], ns = n_send[0] + n_send[1];
+        cbmd_ensure_capacity( ctx, first + nr ); // (pos is not used any more: scratch may move)
+        if ( self )
+        {
+            for ( int k = 0; k < 2; k++ )
+                if ( n_recv[k] > 0 )
+                {
+                    k_halo_make_self<<<div_up( n_recv[k], 256 ), 256, 0, s>>>(
+                        ctx->xt, ctx->id, P[k]->send_idx, n_recv[k], P[k]->recv_first, ctx->n_local, d,
+                        P[k]->shift, ctx->ghost_owner, ctx->ghost_image, ctx->ghost_rank, ctx->rank );
+                    CBMD_LAUNCH_CHECK( ctx );
+                }
         }
         else
         {
-            cbmd_ensure_capacity( ctx, first + P.n_recv );
-            const size_t sb = (size_t)( P.n_send + 1 ) * ( sizeof( XT ) + sizeof( int ) ) + 64;
-            ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, sb, s );
-            XT *sx = (XT *)ctx->sendbuf;
-            int *si = (int *)( sx + P.n_send + 1 );
-            if ( P.n_send > 0 )
-            {
-                k_halo_pack<<<div_up( P.n_send, 256 ), 256, 0, s>>>( ctx->xt, ctx->id, P.send_idx,
-                                                                     P.n_send, sx, si );
-                CBMD_LAUNCH_CHECK( ctx );
-            }
+            ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, (size_t)( ns + 2 ) * sizeof( HaloRec ), s );
+            ensure_buf( ctx->recvbuf, ctx->recvbuf_bytes, (size_t)( nr + 2 ) * sizeof( HaloRec ), s );
+            HaloRec *sx[2] = { (HaloRec *)ctx->sendbuf, (HaloRec *)ctx->sendbuf + n_send[0] };
+            HaloRec *rx[2] = { (HaloRec *)ctx->recvbuf, (HaloRec *)ctx->recvbuf + n_recv[0] };
+            for ( int k = 0; k < 2; k++ )
+                if ( n_send[k] > 0 )
+                {
+                    k_halo_pack_rec<<<div_up( n_send[k], 256 ), 256, 0, s>>>(
+                        ctx->xt, ctx->id, ctx->ghost_owner, ctx->ghost_rank, ctx->ghost_image, P[k]->send_idx,
+                        n_send[k], ctx->n_local, ctx->rank, sx[k] );
+                    CBMD_LAUNCH_CHECK( ctx );
+                }
             CBMD_NCCL( ncclGroupStart() );
-            if ( P.n_send > 0 )
-            {
-                CBMD_NCCL( ncclSend( sx, (size_t)P.n_send * sizeof( XT ), ncclChar, P.peer_send,
-                                     ctx->nccl, s ) );
-                CBMD_NCCL( ncclSend( si, P.n_send, ncclInt, P.peer_send, ctx->nccl, s ) );
-            }
-            if ( P.n_recv > 0 )
-            {
-                // straight into the tail: ghosts of one phase are contiguous
-                CBMD_NCCL( ncclRecv( ctx->xt + first, (size_t)P.n_recv * sizeof( XT ), ncclChar,
-                                     P.peer_recv, ctx->nccl, s ) );
-                CBMD_NCCL( ncclRecv( ctx->id + first, P.n_recv, ncclInt, P.peer_recv, ctx->nccl, s ) );
-            }
+            for ( int k = 0; k < 2; k++ )
+                if ( n_send[k] > 0 )
+                    CBMD_NCCL( ncclSend( sx[k], (size_t)n_send[k] * sizeof( HaloRec ), ncclChar, peer_send[k],
+                                         ctx->nccl, s ) );
+            for ( int k = 0; k < 2; k++ )
+                if ( n_recv[k] > 0 )
+                    CBMD_NCCL( ncclRecv( rx[k], (size_t)n_recv[k] * sizeof( HaloRec ), ncclChar, peer_recv[k],
+                                         ctx->nccl, s ) );
             CBMD_NCCL( ncclGroupEnd() );
-            if ( P.n_recv > 0 && P.shift != 0.0 )
-            {
-                k_halo_shift<<<div_up( P.n_recv, 256 ), 256, 0, s>>>( ctx->xt, first, P.n_recv, d,
-                                                                      P.shift );
-                CBMD_LAUNCH_CHECK( ctx );
-            }
+            for ( int k = 0; k < 2; k++ )
+                if ( n_recv[k] > 0 )
+                {
+                    // ghosts of one phase are contiguous in the tail
+                    k_halo_unpack_rec<<<div_up( n_recv[k], 256 ), 256, 0, s>>>(
+                        rx[k], n_recv[k], P[k]->recv_first, ctx->n_local, d, P[k]->shift, ctx->xt, ctx->id,
+                        ctx->ghost_owner, ctx->ghost_rank, ctx->ghost_image );
+                    CBMD_LAUNCH_CHECK( ctx );
+                }
         }
-        ctx->n_ghost += P.n_recv;
+        ctx->n_ghost += nr;
     }
     // ghost v / f are never communicated (comm_mpi_impl.h:346-347); keep them defined
     if ( ctx->n_ghost > 0 )
@@ -534,6 +809,9 @@ extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
         CBMD_LAUNCH_CHECK( ctx );
     }
     ctx->flat_halo_ok = all_self;
+    ctx->flat_mp_ok = false;
+    if ( !all_self && ctx->halo_stages == 1 )
+        build_flat_plan( ctx );
     ctx->have_halo = true;
     CBMD_API_END
 }
@@ -608,6 +886,42 @@ extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
     {
         CBMD_CUDA( cudaEventRecord( ctx->ev_x, ctx->stream ) );
         CBMD_CUDA( cudaStreamWaitEvent( s, ctx->ev_x, 0 ) );
+    }
+    if ( ctx->flat_mp_ok )
+    {
+        // one stage: pack what the others want, one group with every peer, unpack + shift
+        if ( ctx->n_export > 0 )
+        {
+            k_halo_pack_flat<<<div_up( ctx->n_export, 256 ), 256, 0, s>>>( ctx->xt, ctx->export_idx, ctx->n_export,
+                                                                         ctx->sendbuf );
+            CBMD_LAUNCH_CHECK( ctx );
+        }
+        CBMD_NCCL( ncclGroupStart() );
+        for ( int p = 0; p < ctx->nranks; p++ )
+        {
+            if ( p == ctx->rank )
+                continue;
+            if ( ctx->scnt[p] > 0 )
+                CBMD_NCCL( ncclSend( ctx->sendbuf + 3 * (size_t)ctx->soff[p], 3 * (size_t)ctx->scnt[p], ncclDouble, p,
+                                     ctx->nccl, s ) );
+            if ( ctx->rcnt[p] > 0 )
+                CBMD_NCCL( ncclRecv( ctx->recvbuf + 3 * (size_t)ctx->roff[p], 3 * (size_t)ctx->rcnt[p], ncclDouble, p,
+                                     ctx->nccl, s ) );
+        }
+        CBMD_NCCL( ncclGroupEnd() );
+        const bool live = cbmd_mirror_live( ctx );
+        k_halo_unpack_flat<<<div_up( ctx->n_ghost, 256 ), 256, 0, s>>>(
+            ctx->xt, ctx->n_local, ctx->n_ghost, ctx->ghost_owner, ctx->ghost_rank, ctx->ghost_image, ctx->ghost_slot,
+            ctx->recvbuf, ctx->rank, ctx->gext[0], ctx->gext[1], ctx->gext[2], cbmd_mirror_ptrs( ctx ) );
+        CBMD_LAUNCH_CHECK( ctx );
+        if ( live )
+            ctx->mirror_ghost_epoch = ctx->epoch;
+        if ( ov )
+        {
+            CBMD_CUDA( cudaEventRecord( ctx->ev_halo, s ) );
+            ctx->halo_pending = true;
+        }
+        return 0;
     }
     // The two phases of one dimension are independent of each other: the odd phase never
     // sends what the even phase has just received (cbmd_exchange_halo, comm_mpi_impl.h:301-303).

@@ -167,9 +167,19 @@ struct cbmd_ctx
     HaloPhase phase[6];
     double comm_depth = 0.0;
     bool have_halo = false;
-    int *ghost_owner = nullptr;           // [cap] root owned atom of each ghost (single-rank fast path)
-    unsigned char *ghost_image = nullptr; // [cap] packed image flags
-    bool flat_halo_ok = false;
+    int *ghost_owner = nullptr;           // [cap] index of each ghost's root (owned) atom on its root rank
+    int *ghost_rank = nullptr;            // [cap] root rank of each ghost
+    unsigned char *ghost_image = nullptr; // [cap] packed image flags (accumulated PBC shifts)
+    bool flat_halo_ok = false;            // one rank: every ghost is an image of an owned atom here
+    // multi-rank one-stage refresh (cbmd_comm.cu): ghosts fetched straight from their ROOT rank.
+    // Import side: ghosts rooted on rank p are slots [roff[p], roff[p]+rcnt[p]) of the receive
+    // buffer, in ghost order (ghost_slot[g]); export side: export_idx[soff[p]..+scnt[p]) are the
+    // owned atoms rank p wants every step, in the order rank p expects them.
+    bool flat_mp_ok = false;
+    int *ghost_slot = nullptr; // [cap]
+    int *export_idx = nullptr;
+    int export_cap = 0, n_export = 0, n_import = 0;
+    std::vector<int> rcnt, roff, scnt, soff;
     double *sendbuf = nullptr, *recvbuf = nullptr;
     size_t sendbuf_bytes = 0, recvbuf_bytes = 0;
     // halo/compute overlap (multi-rank): update_halo runs on comm_stream while the force
@@ -180,6 +190,7 @@ struct cbmd_ctx
     cudaEvent_t ev_x = nullptr, ev_halo = nullptr, ev_boundary = nullptr, ev_fready = nullptr;
     bool halo_pending = false; // ghost positions are still in flight on comm_stream
     int overlap = 1;           // option "overlap": 0 keeps everything on one stream
+    int halo_stages = 1;       // option "halo_stages": 1 = one-stage refresh from the root ranks, 3 = per dimension
     int *tile_list = nullptr, *tile_flag = nullptr;
     int tile_cap = 0, n_tiles_interior = 0, n_tiles_boundary = 0;
     bool tiles_valid = false;

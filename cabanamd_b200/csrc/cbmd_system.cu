@@ -72,6 +72,8 @@ void cbmd_ensure_capacity( cbmd_ctx *ctx, int n )
     regrow( ctx->nb_count, used, new_cap, s );
     regrow( ctx->ghost_owner, used, new_cap, s );
     regrow( ctx->ghost_image, used, new_cap, s );
+    regrow( ctx->ghost_rank, used, new_cap, s );
+    realloc_plain( ctx->ghost_slot, new_cap );
     // pure scratch / derived arrays: contents need not survive
     realloc_plain( ctx->xt_alt, new_cap );
     realloc_plain( ctx->v_alt, 3 * (size_t)new_cap );
@@ -223,6 +225,8 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
         ctx->device = device;
         if ( const char *e = getenv( "CBMD_OVERLAP" ) ) // A/B switch for measurements
             ctx->overlap = atoi( e );
+        if ( const char *e = getenv( "CBMD_HALO_STAGES" ) ) // A/B switch: 3 = per-dimension forwarding
+            ctx->halo_stages = atoi( e ) == 3 ? 3 : 1;
         if ( const char *e = getenv( "CBMD_GATHER" ) ) // A/B switch: 0 = 32-byte records by LDG.256
             ctx->gather_mode = atoi( e ) == 0 ? 0 : 1;
         if ( const char *e = getenv( "CBMD_NEIGH_KERNEL" ) ) // A/B switch: 1 = per-thread walk, half-size cells
@@ -291,7 +295,8 @@ extern "C" int cbmd_destroy( cbmd_ctx *ctx )
                      ctx->cell_atoms, ctx->atom_cell,   ctx->perm,       ctx->nb,
                      ctx->nb_count,   ctx->ghost_owner, ctx->ghost_image, ctx->sendbuf,
                      ctx->recvbuf,    ctx->scratch,     ctx->d_red,      ctx->d_flags,
-                     ctx->pe_partial, ctx->tile_list, ctx->tile_flag, ctx->scan_tmp, ctx->cpos };
+                     ctx->pe_partial, ctx->tile_list, ctx->tile_flag, ctx->scan_tmp, ctx->cpos,
+                     ctx->ghost_rank, ctx->ghost_slot, ctx->export_idx };
     for ( void *p : ptrs )
         if ( p )
             cudaFree( p );
@@ -330,6 +335,14 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
     std::string n( name ? name : "" );
     if ( n == "overlap" )
         ctx->overlap = (int)value;
+    else if ( n == "halo_stages" )
+    {
+        // multi-rank ghost refresh: 1 = every ghost straight from its root rank in one NCCL
+        // group (default); 3 = the reference's forwarding scheme, one group per dimension
+        if ( (int)value != 1 && (int)value != 3 )
+            throw CbmdError( "halo_stages must be 1 or 3" );
+        ctx->halo_stages = (int)value;
+    }
     else if ( n == "gather" )
     {
         if ( (int)value != 0 && (int)value != 1 )
