@@ -154,6 +154,7 @@ struct cbmd_ctx
     cudaTextureObject_t tex_nb = 0; // the table as 16-byte texels (index stream of the FP32 sweep)
     int *nb = nullptr;
     size_t nb_alloc = 0;
+    int row_order = 0;         // option "row_order": 1 = bank-aware (Latin) order of full-list rows, 0 = index order
     int neigh_kernel = 0;      // option "neigh_kernel": 0 = staged 27-cell stencil, 1 = per-thread walk over half-size cells
     float4 *cpos = nullptr;    // candidates packed in cell order for the walk kernel
     int cpos_cap = 0;

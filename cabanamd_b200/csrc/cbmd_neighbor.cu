@@ -446,6 +446,142 @@ __global__ void __launch_bounds__( 128 )
         atomicMax( d_max, mx );
 }
 
+// ---------------------------------------------------------------------------
+// k_rows_bank_order (option "row_order" 1; NOT the default, see the end of this comment):
+// bank-aware order of every row.
+//
+// The full-list sweeps gather x_j with LDG.128: L1 serves such a request in groups of eight
+// lanes, and a group costs as many passes as its worst conflict on the POSITION of the 16-byte
+// word inside its 128-byte line, j & 7 (round 1, experiments/ldg_patterns.cu).  Rows in index
+// order leave that to chance.  Here lane q (= i & 7) of a group takes, at step r, a neighbour
+// of class (r + q) & 7: a Latin square — the eight lanes of a group read eight different
+// positions for as long as all classes last; when a class runs out the entry comes from the
+// class with most entries left.  The SET of a row does not change, only its order (sums
+// differ by round-off from the index-ordered row's; every run orders the same way).
+// Measured on B200, 4 M atoms (profiles/r2_force_variants_b4.txt, profiles/r2_row_order.txt):
+// FP64 sweep 0.688 -> 0.658 ms (roofline 0.322 -> 0.337), FP32 sweep 0.469 -> 0.407 ms (0.439 ->
+// 0.506).  The pass itself takes 2.4 ms per rebuild (three dependent per-lane walks over the
+// staged row), 20 sweeps gain 0.6 ms (FP64) / 1.2 ms (FP32): a net loss at the reference's
+// rebuild period of 20 steps, so the default keeps the rows in index order.
+//
+// One warp per 32-atom tile, whole tile block staged in shared memory: bucket every lane's
+// row by class (stable), deal it out in Latin order, write the block back coalesced.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__( 128 )
+    k_rows_bank_order( int4 *__restrict__ nb4, const int *__restrict__ nb_count, int rows4, int n_local )
+{
+    extern __shared__ int sm[]; // [4 warps][2][rows4*4][32]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tile = blockIdx.x * 4 + w;
+    if ( tile * 32 >= n_local )
+        return;
+    const int i = tile * 32 + lane;
+    const int rows = rows4 * 4;
+    int *s0 = sm + (size_t)w * 2 * rows * 32, *s1 = s0 + rows * 32;
+    const int c = i < n_local ? min( nb_count[i], rows ) : 0;
+    int cmax = c;
+    for ( int o = 16; o > 0; o >>= 1 )
+        cmax = max( cmax, __shfl_xor_sync( 0xffffffffu, cmax, o ) );
+    const int c4max = ( cmax + 3 ) >> 2;
+    int4 *p = nb4 + ( (size_t)tile * rows4 ) * 32 + lane;
+    const int q = i & 7;
+    // 1. load the block (coalesced), column of lane l at s0[n*32 + l]; class sizes in packed bytes
+    //    (class relative to the lane: (j - q) & 7; classes 0-3 in lo, 4-7 in hi)
+    unsigned lo = 0u, hi = 0u;
+    for ( int k4 = 0; k4 < c4max; k4++ )
+    {
+        const int4 v = p[k4 * 32];
+        const int jj[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for ( int u = 0; u < 4; u++ )
+        {
+            const int n = 4 * k4 + u;
+            s0[n * 32 + lane] = jj[u];
+            if ( n < c )
+            {
+                const int cl = ( jj[u] - q ) & 7;
+                if ( cl < 4 )
+                    lo += 1u << ( 8 * cl );
+                else
+                    hi += 1u << ( 8 * ( cl - 4 ) );
+            }
+        }
+    }
+    // 2. stable bucket by class into s1: bucket start = sum of the sizes of the lower classes
+    unsigned off_lo, off_hi; // running write offsets per class, packed bytes
+    {
+        unsigned acc = 0u, t;
+        off_lo = 0u;
+#pragma unroll
+        for ( int b = 0; b < 4; b++ )
+        {
+            off_lo |= acc << ( 8 * b );
+            t = ( lo >> ( 8 * b ) ) & 0xffu;
+            acc += t;
+        }
+        off_hi = 0u;
+#pragma unroll
+        for ( int b = 0; b < 4; b++ )
+        {
+            off_hi |= acc << ( 8 * b );
+            t = ( hi >> ( 8 * b ) ) & 0xffu;
+            acc += t;
+        }
+    }
+    const unsigned start_lo = off_lo, start_hi = off_hi;
+    for ( int n = 0; n < c; n++ )
+    {
+        const int j = s0[n * 32 + lane];
+        const int cl = ( j - q ) & 7;
+        const unsigned sh = 8 * ( cl & 3 );
+        const unsigned o = ( ( cl < 4 ? off_lo : off_hi ) >> sh ) & 0xffu;
+        s1[o * 32 + lane] = j;
+        if ( cl < 4 )
+            off_lo += 1u << sh;
+        else
+            off_hi += 1u << sh;
+    }
+    // 3. deal out: step r wants relative class r & 7; exhausted -> the class with most left
+    unsigned used_lo = 0u, used_hi = 0u; // entries taken per class
+    for ( int r = 0; r < c; r++ )
+    {
+        int cl = r & 7;
+        unsigned sh = 8 * ( cl & 3 );
+        unsigned left = ( ( ( cl < 4 ? lo : hi ) >> sh ) & 0xffu ) - ( ( ( cl < 4 ? used_lo : used_hi ) >> sh ) & 0xffu );
+        if ( left == 0u )
+        {
+            // per-class remaining counts, byte-wise; pick the largest (lowest class on ties)
+            const unsigned rl = __vsub4( lo, used_lo ), rh = __vsub4( hi, used_hi );
+            unsigned best = 0u;
+            cl = 0;
+#pragma unroll
+            for ( int b = 0; b < 8; b++ )
+            {
+                const unsigned v = ( ( b < 4 ? rl : rh ) >> ( 8 * ( b & 3 ) ) ) & 0xffu;
+                if ( v > best )
+                {
+                    best = v;
+                    cl = b;
+                }
+            }
+            sh = 8 * ( cl & 3 );
+        }
+        const unsigned st = ( ( cl < 4 ? start_lo : start_hi ) >> sh ) & 0xffu;
+        const unsigned us = ( ( cl < 4 ? used_lo : used_hi ) >> sh ) & 0xffu;
+        s0[r * 32 + lane] = s1[( st + us ) * 32 + lane];
+        if ( cl < 4 )
+            used_lo += 1u << sh;
+        else
+            used_hi += 1u << sh;
+    }
+    // (the padding entries c .. 4*ceil(c/4) of s0 still hold the atom's own index)
+    __syncwarp();
+    const int c4 = ( c + 3 ) >> 2;
+    for ( int k4 = 0; k4 < c4; k4++ )
+        p[k4 * 32] = make_int4( s0[( 4 * k4 ) * 32 + lane], s0[( 4 * k4 + 1 ) * 32 + lane],
+                                s0[( 4 * k4 + 2 ) * 32 + lane], s0[( 4 * k4 + 3 ) * 32 + lane] );
+}
+
 __global__ void __launch_bounds__( 256 )
     k_nb_to_csr( const int *__restrict__ nb, int nb_rows,
                  const int *__restrict__ nb_count, const int64_t *__restrict__ offsets, int n_local,
@@ -685,6 +821,20 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
         CBMD_REQUIRE( attempt < 2, "neighbour list did not converge" );
     }
     ctx->nb_max = observed;
+    // bank-aware row order for the LDG.128 gathers of the full-list sweeps (byte counters: rows
+    // of at most 255 entries; the shared-memory staging bounds the row capacity as well)
+    if ( ctx->row_order == 1 && !half && n_local > 0 && rows <= 252 )
+    {
+        const size_t smb = (size_t)4 * 2 * rows * 32 * sizeof( int );
+        if ( smb <= 200 * 1024 )
+        {
+            if ( smb > 48 * 1024 )
+                CBMD_CUDA( cudaFuncSetAttribute( k_rows_bank_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb ) );
+            k_rows_bank_order<<<div_up( div_up( n_local, 32 ), 4 ), 128, smb, s>>>( (int4 *)ctx->nb, ctx->nb_count, rows >> 2,
+                                                                                n_local );
+            CBMD_LAUNCH_CHECK( ctx );
+        }
+    }
     build_tile_lists( ctx, rcut );
     // neighbor_verlet.h:60-61: max_neigh_guess = current_max * 1.1 when exceeded
     int guess = max_neigh_guess;

@@ -229,6 +229,8 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
             ctx->halo_stages = atoi( e ) == 3 ? 3 : 1;
         if ( const char *e = getenv( "CBMD_GATHER" ) ) // A/B switch: 0 = 32-byte records by LDG.256
             ctx->gather_mode = atoi( e ) == 0 ? 0 : 1;
+        if ( const char *e = getenv( "CBMD_ROW_ORDER" ) ) // A/B switch: 1 = bank-aware row order
+            ctx->row_order = atoi( e ) == 1 ? 1 : 0;
         if ( const char *e = getenv( "CBMD_NEIGH_KERNEL" ) ) // A/B switch: 1 = per-thread walk, half-size cells
             ctx->neigh_kernel = atoi( e ) == 1 ? 1 : 0;
         if ( const char *e = getenv( "CBMD_PRECISION" ) ) // 32 = FP32 pair arithmetic (full lists)
@@ -348,6 +350,14 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
         if ( (int)value != 0 && (int)value != 1 )
             throw CbmdError( "gather must be 0 (32-byte records by LDG.256) or 1 (mirror: xy LDG.128 + z TEX, FP32 float4)" );
         ctx->gather_mode = (int)value;
+    }
+    else if ( n == "row_order" )
+    {
+        // order of the entries inside a full-list row (next cbmd_neigh_build): 0 = ascending
+        // (cell, index) (default), 1 = bank-aware Latin order for the LDG.128 gathers
+        if ( (int)value != 0 && (int)value != 1 )
+            throw CbmdError( "row_order must be 0 or 1" );
+        ctx->row_order = (int)value;
     }
     else if ( n == "neigh_kernel" )
     {

@@ -182,12 +182,16 @@ extern "C"
      *               positions — the reference's T_X_FLOAT/T_F_FLOAT = float variant
      *               (src/types.h:133-148) for the force evaluation; integration state stays FP64.
      *               Forces agree with an FP32 evaluation of the same list to ~1e-6 relative.
+     *   "row_order" 0 (default) rows in ascending (cell, index) order; 1 = full-list rows re-ordered
+     *               after the build in a bank-aware (Latin) order: the eight lanes of an LDG.128
+     *               group gather from eight different 16-byte positions (faster sweeps, but the
+     *               re-ordering pass costs more than 20 sweeps gain).  Same sets.
      *   "neigh_kernel" 0 (default) Verlet build by a warp per cell over a staged 27-cell stencil;
      *               1 = one thread per atom walking a 5x5x5 stencil of half-size cells (faster
      *               build, rows in an order the force sweep likes less).  Same sets.
      *   "overlap"   1 (default) halo refresh on a second stream under the interior force tiles
      * Environment overrides read at cbmd_create: CBMD_GATHER, CBMD_PRECISION, CBMD_NEIGH_KERNEL,
-     * CBMD_OVERLAP. */
+     * CBMD_ROW_ORDER, CBMD_HALO_STAGES, CBMD_OVERLAP. */
     int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value );
 
 #ifdef __cplusplus
