@@ -158,7 +158,12 @@ struct cbmd_ctx
     int neigh_kernel = 0;      // option "neigh_kernel": 0 = staged 27-cell stencil, 1 = per-thread walk over half-size cells
     float4 *cpos = nullptr;    // candidates packed in cell order for the walk kernel
     int cpos_cap = 0;
-    int *nb_count = nullptr; // [cap]
+    int *nb_count = nullptr; // [cap] entries per row
+    // PULL table (half list for the atomics-free Newton-3 sweep, cbmd_neighbor.cu sweep_group MODE 2)
+    bool nb_pull = false;
+    int *nb_count_i = nullptr; // [cap] length of the reference half row (entries without NB_JSIDE)
+    int pull_rows_hint = 0;
+    int half_kernel = 1;       // option "half_kernel": 1 = atomics-free pull sweep (default), 0 = RED.ADD.F64 scatter
     int nb_max = 0;          // max row length of the last build
     double nb_rcut = 0.0;
 
@@ -425,6 +430,12 @@ __host__ __device__ __forceinline__ size_t nb_entry( int i, int n, int rows )
 }
 // table elements needed for `stride` (multiple of 32) atoms
 __host__ __device__ __forceinline__ size_t nb_table_size( int stride, int rows ) { return (size_t)stride * (size_t)rows; }
+
+// PULL tables (half lists of the atomics-free Newton-3 sweep): an entry is the neighbour's index,
+// flagged with NB_JSIDE when the pair is stored in the NEIGHBOUR's half row (it is listed here
+// only so that this atom can pull its share of that pair)
+#define NB_JSIDE ( 1 << 30 )
+#define NB_INDEX_MASK 0x3fffffff
 
 // store a position into whichever mirror parts exist (kernels that write xt call this)
 __device__ __forceinline__ void mirror_store( const MirrorPtrs &m, int i, const XT &r )

@@ -49,32 +49,50 @@ __device__ __forceinline__ bool half_valid( const XT &a, const XT &b )
 // ---------------------------------------------------------------------------
 // K staged candidates against this lane's atom: FP32 decisions, ONE warp vote for the
 // (rare) exact FP64 re-evaluation, then in-order, branch-free appends to the lane's row.
-template <bool HALF, int K>
+// MODE 0: full list (i != j).  MODE 1: half list (reference HalfNeighborTag).  MODE 2: PULL rows
+// for the atomics-free Newton-3 sweep (cbmd_force.cu): the row of an OWNED atom i holds its half
+// row (x_j > x_i, any j) plus, flagged with NB_JSIDE, the owned atoms j < i in that order whose
+// half row holds i; the row of a GHOST atom holds only the flagged kind.  Stripped of the
+// flagged entries the rows ARE the reference's half list (cbmd_neigh_get does that).
+template <int MODE, int K>
 __device__ __forceinline__ void
 sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const XT &xi, float xr,
              float yr, float zr, int i, float r2lo, float r2hi, float tolx, double rsqr,
-             char *row0, int nb_rows, int &count )
+             char *row0, int nb_rows, int &count, int n_local, int &count_i )
 {
     // i < 0 marks an inactive lane: its r2lo/r2hi are -1 so nothing is ever accepted
     float4 c[K];
 #pragma unroll
     for ( int k = 0; k < K; k++ )
         c[k] = cand[k];
-    bool ok[K], amb[K];
+    bool ok[K], amb[K], js[K];
     bool any_amb = false;
+    const bool iown = i < n_local;
 #pragma unroll
     for ( int k = 0; k < K; k++ )
     {
         const float fx = c[k].x - xr, fy = c[k].y - yr, fz = c[k].z - zr;
         const float d2 = fx * fx + fy * fy + fz * fz;
-        const bool ns = __float_as_int( c[k].w ) != i;
+        const int j = __float_as_int( c[k].w );
+        const bool ns = j != i;
         ok[k] = ns && ( d2 < r2lo );
         amb[k] = ns && ( d2 < r2hi );
-        if ( HALF )
+        js[k] = false;
+        if ( MODE == 1 )
         {
             // xj > xi decided in FP32 unless |xj - xi| is within its error
             ok[k] = ok[k] && ( fx > tolx );
             amb[k] = amb[k] && ( fx >= -tolx );
+        }
+        if ( MODE == 2 )
+        {
+            const bool up = fx > tolx, dn = fx < -tolx, jown = j < n_local;
+            // i side: owned i, x_j > x_i;  j side: owned j, x_j < x_i
+            const bool keep = ( iown && up ) || ( jown && dn );
+            const bool drop = ( up && !iown ) || ( dn && !jown ) || ( !iown && !jown );
+            ok[k] = ok[k] && keep;
+            amb[k] = amb[k] && !drop;
+            js[k] = dn;
         }
         amb[k] = amb[k] && !ok[k];
         any_amb = any_amb || amb[k];
@@ -85,11 +103,18 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
         for ( int k = 0; k < K; k++ )
             if ( amb[k] )
             { // exact re-evaluation of the reference criterion (rare)
-                const XT xj = ld_xt( xt + __float_as_int( c[k].w ) );
+                const int j = __float_as_int( c[k].w );
+                const XT xj = ld_xt( xt + j );
                 ok[k] = dist2_exact( __dsub_rn( xi.x, xj.x ), __dsub_rn( xi.y, xj.y ),
                                      __dsub_rn( xi.z, xj.z ) ) <= rsqr;
-                if ( HALF )
+                if ( MODE == 1 )
                     ok[k] = ok[k] && half_valid( xi, xj );
+                if ( MODE == 2 )
+                {
+                    const bool up = half_valid( xi, xj ), dn = half_valid( xj, xi );
+                    ok[k] = ok[k] && ( ( iown && up ) || ( j < n_local && dn ) );
+                    js[k] = dn;
+                }
             }
     }
 #pragma unroll
@@ -100,11 +125,16 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
         const int st = ( ok[k] && count < nb_rows ) ? 1 : 0;
         const unsigned off = ( ( (unsigned)count >> 2 ) << 9 ) + ( ( (unsigned)count & 3u ) << 2 );
         char *dst = row0 + (unsigned long long)off;
+        int val = __float_as_int( c[k].w );
+        if ( MODE == 2 )
+            val |= js[k] ? NB_JSIDE : 0;
         asm volatile( "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b32 [%0], %1;\n\t}"
                       :
-                      : "l"( dst ), "r"( __float_as_int( c[k].w ) ), "r"( st )
+                      : "l"( dst ), "r"( val ), "r"( st )
                       : "memory" );
         count += ok[k] ? 1 : 0;
+        if ( MODE == 2 )
+            count_i += ( ok[k] && !js[k] ) ? 1 : 0;
     }
 }
 
@@ -112,12 +142,12 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
 #define NB_THREADS ( 32 * NBC )
 #define NB_STAGE 1280 // candidates per staging chunk (20 KB)
 
-template <bool HALF>
+template <int MODE>
 __global__ void __launch_bounds__( NB_THREADS )
     k_neigh_build( const XT *__restrict__ xt, int n_local, GridDesc g,
                    const int *__restrict__ cell_start, const int *__restrict__ cell_atoms,
                    double rsqr, double3 centre, int *__restrict__ nb, int nb_stride, int nb_rows,
-                   int *__restrict__ nb_count, int *__restrict__ d_max )
+                   int *__restrict__ nb_count, int *__restrict__ d_max, int *__restrict__ nb_count_i )
 {
     __shared__ float4 cand[NB_STAGE];
     __shared__ int run_src[9], run_off[10];
@@ -139,7 +169,8 @@ __global__ void __launch_bounds__( NB_THREADS )
         cs = cell_start[colrow + cc];
         ce = cell_start[colrow + cc + 1];
     }
-    const bool has_owned = ( ce > cs ) && ( cell_atoms[cs] < n_local );
+    // rows are made for the owned atoms; the pull rows also for the ghosts
+    const bool has_owned = ( ce > cs ) && ( MODE == 2 || cell_atoms[cs] < n_local );
     if ( !__syncthreads_or( has_owned ) )
         return;
 
@@ -214,7 +245,7 @@ __global__ void __launch_bounds__( NB_THREADS )
         if ( s < ce )
         {
             i = cell_atoms[s];
-            if ( i >= n_local )
+            if ( MODE != 2 && i >= n_local )
                 i = -1;
         }
         const bool active = i >= 0;
@@ -227,7 +258,7 @@ __global__ void __launch_bounds__( NB_THREADS )
         const float xr = active ? (float)( xi.x - ox ) : 0.f, yr = active ? (float)( xi.y - oy ) : 0.f,
                     zr = active ? (float)( xi.z - oz ) : 0.f;
         char *const row0 = (char *)( nb + nb_tile_base( active ? i : 0, nb_rows ) );
-        int count = 0;
+        int count = 0, count_i = 0;
 
         for ( int chunk = 0; chunk < total; chunk += NB_STAGE )
         {
@@ -283,25 +314,34 @@ __global__ void __launch_bounds__( NB_THREADS )
                 const int n4 = ( e - b ) >> 2;
                 const float4 *cp = cand + b;
                 for ( int q = 0; q < n4; q++, cp += 4 )
-                    sweep_group<HALF, 4>( cp, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx, rsqr,
-                                                   row0, nb_rows, count );
+                    sweep_group<MODE, 4>( cp, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx, rsqr,
+                                          row0, nb_rows, count, n_local, count_i );
                 for ( int t = b + 4 * n4; t < e; t++ )
-                    sweep_group<HALF, 1>( cand + t, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx,
-                                                   rsqr, row0, nb_rows, count );
+                    sweep_group<MODE, 1>( cand + t, xt, xi, xr, yr, zr, i, r2lo_l, r2hi_l, tolx,
+                                          rsqr, row0, nb_rows, count, n_local, count_i );
             }
         }
         if ( active )
         {
             nb_count[i] = count;
+            if ( MODE == 2 )
+                nb_count_i[i] = count_i;
             // pad the row to a multiple of four with the atom itself (never a neighbour)
             for ( int k = count; k < min( ( count + 3 ) & ~3, nb_rows ); k++ )
                 *(int *)( row0 + ( ( (unsigned)k >> 2 ) << 9 ) + ( ( (unsigned)k & 3u ) << 2 ) ) = i;
         }
-        int mx = count;
+        int mx = count, mi = count_i;
         for ( int o = 16; o > 0; o >>= 1 )
+        {
             mx = max( mx, __shfl_xor_sync( 0xffffffffu, mx, o ) );
+            mi = max( mi, __shfl_xor_sync( 0xffffffffu, mi, o ) );
+        }
         if ( lane == 0 && mx > 0 )
+        {
             atomicMax( d_max, mx );
+            if ( MODE == 2 )
+                atomicMax( d_max + 1, mi ); // longest reference row (without the j-side entries)
+        }
     }
 }
 
@@ -591,9 +631,13 @@ __global__ void __launch_bounds__( 256 )
     if ( i >= n_local )
         return;
     const int c = nb_count[i];
-    const int64_t o = offsets[i];
+    int64_t o = offsets[i];
     for ( int n = 0; n < c; n++ )
-        csr[o + n] = nb[nb_entry( i, n, nb_rows )];
+    {
+        const int e = nb[nb_entry( i, n, nb_rows )];
+        if ( !( e & NB_JSIDE ) ) // pull rows: the flagged entries are not part of the reference row
+            csr[o++] = e;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -697,7 +741,10 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
     // the edge cells, which keeps |cell(i)-cell(j)| <= 1 for every pair within rcut.
     // option "neigh_kernel" 0 (default): cells >= rcut, one halo layer, staged 27-cell stencil;
     // 1: cells >= rcut/2, two halo layers, 5x5x5 stencil walked by one thread per atom
-    const bool walk = ctx->neigh_kernel == 1;
+    // half lists for the atomics-free Newton-3 sweep get PULL rows (sweep_group MODE 2): rows for
+    // owned and ghost atoms, built by the staged kernel
+    const bool pull = half && ctx->half_kernel == 1;
+    const bool walk = ctx->neigh_kernel == 1 && !pull;
     const double cell = walk ? 0.5 * rcut : rcut;
     const double din[3] = { cell, cell, cell };
     int nbin[3];
@@ -718,16 +765,23 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
     ctx->nb_rcut = rcut;
     ctx->nb_n = n_local;
     ctx->nb_ntot = n_total;
+    ctx->nb_pull = pull;
     int rows = ( ( max_neigh_guess > 0 ? max_neigh_guess : 1 ) + 3 ) & ~3;
-    const int stride = ( n_local + 31 ) & ~31;
+    if ( pull ) // a pull row holds both sides of the atom's pairs: about twice the half row
+        rows = std::max( ctx->pull_rows_hint, ( 2 * rows + 8 + 3 ) & ~3 );
+    const int stride = ( ( pull ? n_total : n_local ) + 31 ) & ~31;
     const double rsqr = rcut * rcut;
     const double3 centre = make_double3( 0.5 * ( ctx->llo[0] + ctx->lhi[0] ),
                                          0.5 * ( ctx->llo[1] + ctx->lhi[1] ),
                                          0.5 * ( ctx->llo[2] + ctx->lhi[2] ) );
-    int *d_max = ctx->d_flags;
+    int *d_max = ctx->d_flags; // [0] longest row, [1] longest reference row of a pull table
     int *d_mag = ctx->d_flags + 9;
     if ( n_total > 0 )
+    {
         CBMD_CUDA( cudaMemsetAsync( ctx->nb_count, 0, (size_t)n_total * sizeof( int ), s ) );
+        if ( pull )
+            CBMD_CUDA( cudaMemsetAsync( ctx->nb_count_i, 0, (size_t)n_total * sizeof( int ), s ) );
+    }
     if ( walk && n_total > 0 )
     {
         // candidates packed in cell order: {x,y,z relative to the box centre as FP32, index}
@@ -780,7 +834,7 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
         }
         ctx->nb_rows = rows;
         ctx->nb_stride = stride;
-        CBMD_CUDA( cudaMemsetAsync( d_max, 0, sizeof( int ), s ) );
+        CBMD_CUDA( cudaMemsetAsync( d_max, 0, 2 * sizeof( int ), s ) );
         if ( n_local > 0 && walk )
         {
             if ( half )
@@ -796,24 +850,34 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
         else if ( n_local > 0 )
         {
             const int blocks = g.n[0] * g.n[1] * ( ( g.n[2] + NBC - 1 ) / NBC );
-#define NB_LAUNCH( H )                                                                            \
-    k_neigh_build<H><<<blocks, NB_THREADS, 0, s>>>( ctx->xt, n_local, g, ctx->cell_start,         \
-                                                    ctx->cell_atoms, rsqr, centre, ctx->nb, stride, \
-                                                    rows, ctx->nb_count, d_max )
-            if ( half )
-                NB_LAUNCH( true );
+#define NB_LAUNCH( MODE )                                                                         \
+    k_neigh_build<MODE><<<blocks, NB_THREADS, 0, s>>>( ctx->xt, n_local, g, ctx->cell_start,      \
+                                                       ctx->cell_atoms, rsqr, centre, ctx->nb,    \
+                                                       stride, rows, ctx->nb_count, d_max,        \
+                                                       ctx->nb_count_i )
+            if ( pull )
+                NB_LAUNCH( 2 );
+            else if ( half )
+                NB_LAUNCH( 1 );
             else
-                NB_LAUNCH( false );
+                NB_LAUNCH( 0 );
 #undef NB_LAUNCH
             CBMD_LAUNCH_CHECK( ctx );
         }
         // NeighborList<>::maxNeighbor (neighbor_verlet.h:58-59)
-        CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i, d_max, sizeof( int ), cudaMemcpyDeviceToHost,
+        CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i, d_max, 2 * sizeof( int ), cudaMemcpyDeviceToHost,
                                     s ) );
         CBMD_CUDA( cudaStreamSynchronize( s ) );
         observed = ctx->h_pinned_i[0];
         if ( observed <= rows )
+        {
+            if ( pull )
+            {
+                ctx->pull_rows_hint = std::max( ctx->pull_rows_hint, ( observed + observed / 8 + 3 ) & ~3 );
+                observed = ctx->h_pinned_i[1]; // what the reference's maxNeighbor reports
+            }
             break;
+        }
         rows = (int)( observed * 1.1 ); // [Cabana] 2-D regrow + refill
         if ( rows < observed )
             rows = observed;
@@ -855,9 +919,11 @@ extern "C" int cbmd_neigh_get( cbmd_ctx *ctx, int *counts, int64_t *offsets, int
     std::vector<int> hc( n_total > 0 ? n_total : 1 );
     if ( n_total > 0 )
     {
-        CBMD_CUDA( cudaMemcpyAsync( hc.data(), ctx->nb_count, (size_t)n_total * sizeof( int ),
-                                    cudaMemcpyDeviceToHost, s ) );
+        CBMD_CUDA( cudaMemcpyAsync( hc.data(), ctx->nb_pull ? ctx->nb_count_i : ctx->nb_count,
+                                    (size_t)n_total * sizeof( int ), cudaMemcpyDeviceToHost, s ) );
         CBMD_CUDA( cudaStreamSynchronize( s ) );
+        if ( ctx->nb_pull ) // ghost rows of a pull table hold only j-side entries
+            std::fill( hc.begin() + n_local, hc.end(), 0 );
     }
     std::vector<int64_t> ho( n_local + 1, 0 );
     for ( int i = 0; i < n_local; i++ )
@@ -906,8 +972,8 @@ extern "C" int cbmd_neigh_sizes( cbmd_ctx *ctx, int64_t *total, int *max_neigh )
         int64_t t = 0;
         if ( n_local > 0 )
         {
-            CBMD_CUDA( cudaMemcpyAsync( hc.data(), ctx->nb_count, (size_t)n_local * sizeof( int ),
-                                        cudaMemcpyDeviceToHost, ctx->stream ) );
+            CBMD_CUDA( cudaMemcpyAsync( hc.data(), ctx->nb_pull ? ctx->nb_count_i : ctx->nb_count,
+                                        (size_t)n_local * sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ) );
             CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );
             for ( int i = 0; i < n_local; i++ )
                 t += hc[i];

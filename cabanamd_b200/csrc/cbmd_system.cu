@@ -70,6 +70,7 @@ void cbmd_ensure_capacity( cbmd_ctx *ctx, int n )
     regrow( ctx->id, used, new_cap, s );
     regrow( ctx->q, used, new_cap, s );
     regrow( ctx->nb_count, used, new_cap, s );
+    regrow( ctx->nb_count_i, used, new_cap, s );
     regrow( ctx->ghost_owner, used, new_cap, s );
     regrow( ctx->ghost_image, used, new_cap, s );
     regrow( ctx->ghost_rank, used, new_cap, s );
@@ -229,6 +230,8 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
             ctx->halo_stages = atoi( e ) == 3 ? 3 : 1;
         if ( const char *e = getenv( "CBMD_GATHER" ) ) // A/B switch: 0 = 32-byte records by LDG.256
             ctx->gather_mode = atoi( e ) == 0 ? 0 : 1;
+        if ( const char *e = getenv( "CBMD_HALF_KERNEL" ) ) // A/B switch: 0 = RED.ADD.F64 scatter
+            ctx->half_kernel = atoi( e ) == 0 ? 0 : 1;
         if ( const char *e = getenv( "CBMD_ROW_ORDER" ) ) // A/B switch: 1 = bank-aware row order
             ctx->row_order = atoi( e ) == 1 ? 1 : 0;
         if ( const char *e = getenv( "CBMD_NEIGH_KERNEL" ) ) // A/B switch: 1 = per-thread walk, half-size cells
@@ -298,7 +301,7 @@ extern "C" int cbmd_destroy( cbmd_ctx *ctx )
                      ctx->nb_count,   ctx->ghost_owner, ctx->ghost_image, ctx->sendbuf,
                      ctx->recvbuf,    ctx->scratch,     ctx->d_red,      ctx->d_flags,
                      ctx->pe_partial, ctx->tile_list, ctx->tile_flag, ctx->scan_tmp, ctx->cpos,
-                     ctx->ghost_rank, ctx->ghost_slot, ctx->export_idx };
+                     ctx->ghost_rank, ctx->ghost_slot, ctx->export_idx, ctx->nb_count_i };
     for ( void *p : ptrs )
         if ( p )
             cudaFree( p );
@@ -350,6 +353,14 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
         if ( (int)value != 0 && (int)value != 1 )
             throw CbmdError( "gather must be 0 (32-byte records by LDG.256) or 1 (mirror: xy LDG.128 + z TEX, FP32 float4)" );
         ctx->gather_mode = (int)value;
+    }
+    else if ( n == "half_kernel" )
+    {
+        // Newton-3 sweep (takes effect at the next cbmd_neigh_build): 1 = pull rows, no atomics,
+        // deterministic (default); 0 = scatter f_j with RED.ADD.F64 (round 1)
+        if ( (int)value != 0 && (int)value != 1 )
+            throw CbmdError( "half_kernel must be 0 or 1" );
+        ctx->half_kernel = (int)value;
     }
     else if ( n == "row_order" )
     {

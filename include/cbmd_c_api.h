@@ -182,6 +182,11 @@ extern "C"
      *               positions — the reference's T_X_FLOAT/T_F_FLOAT = float variant
      *               (src/types.h:133-148) for the force evaluation; integration state stays FP64.
      *               Forces agree with an FP32 evaluation of the same list to ~1e-6 relative.
+     *   "half_kernel" 1 (default) Newton-3 sweep without atomics: the half list is stored as PULL
+     *               rows (every atom's own half row + the rows that hold it), each force entry is
+     *               written by one thread in a fixed order; 0 = scatter with RED.ADD.F64.  Takes
+     *               effect at the next cbmd_neigh_build; cbmd_neigh_get returns the reference's
+     *               half list either way.
      *   "row_order" 0 (default) rows in ascending (cell, index) order; 1 = full-list rows re-ordered
      *               after the build in a bank-aware (Latin) order: the eight lanes of an LDG.128
      *               group gather from eight different 16-byte positions (faster sweeps, but the
@@ -191,7 +196,7 @@ extern "C"
      *               build, rows in an order the force sweep likes less).  Same sets.
      *   "overlap"   1 (default) halo refresh on a second stream under the interior force tiles
      * Environment overrides read at cbmd_create: CBMD_GATHER, CBMD_PRECISION, CBMD_NEIGH_KERNEL,
-     * CBMD_ROW_ORDER, CBMD_HALO_STAGES, CBMD_OVERLAP. */
+     * CBMD_ROW_ORDER, CBMD_HALF_KERNEL, CBMD_HALO_STAGES, CBMD_OVERLAP. */
     int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value );
 
 #ifdef __cplusplus

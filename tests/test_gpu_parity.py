@@ -239,6 +239,45 @@ def test_multitype_force(cb, gather):
     assert np.array_equal(ctx.get_atoms()["f"], a["f"])
 
 
+def test_half_list_pull_sweep_is_atomics_free_and_deterministic(cb):
+    """Newton-3 sweep: the default pulls the j side from the transposed list (no atomics).  It must
+    agree with the oracle's half-list forces (owned AND ghost rows, before the reverse fold) to
+    1e-10, conserve momentum, give bit-identical results run after run, and match the round-1
+    RED.ADD.F64 scatter kernel (option half_kernel 0) to round-off."""
+    s = melted_state((10, 10, 10), 60, True)
+    d = s.get()
+    n, ng = d["n_local"], d["n_ghost"]
+    dom = s.domain()
+    lj1, lj2, cutsq = s.tables
+    oc, oo, on = s.list()
+    ol = O.NeighList().set(n, n + ng, oc, oo, on)
+    f_ref = ol.force(d["x"], d["type"], True, lj1, lj2, cutsq)
+    e_ref = ol.energy(d["x"], d["type"], True, lj1, lj2, cutsq)
+    out = {}
+    for kernel in (1, 1, 0):
+        ctx = cb.Context(0)
+        ctx.set_mass([2.0])
+        ctx.set_lj(lj1, lj2, cutsq)
+        ctx.set_domain(dom["llo"], dom["lhi"])
+        ctx.set_atoms(d["x"][:n], d["v"][:n], None, d["type"][:n], d["id"][:n])
+        ctx.append_ghosts(d["x"][n:], d["type"][n:], d["id"][n:])
+        ctx.set_option("half_kernel", kernel)
+        ctx.neigh_build(2.8, True, 0, 50)
+        ctx.zero_force()
+        ctx.request_energy()
+        ctx.force(True)
+        f = ctx.get_atoms()["f"]
+        pe, _ = ctx.energy(True)
+        scale = np.abs(f_ref).max()
+        assert np.abs(f - f_ref).max() <= FORCE_RTOL * scale, kernel
+        assert np.abs(f.sum(0)).max() <= 1e-9 * scale          # Newton 3: owned + ghost rows cancel
+        assert abs(pe - e_ref) <= 1e-12 * abs(e_ref)
+        out.setdefault(kernel, []).append(f)
+        ctx.close()
+    assert np.array_equal(out[1][0], out[1][1])                 # same bits, run after run
+    assert np.abs(out[1][0] - out[0][0]).max() <= 1e-12 * np.abs(f_ref).max()
+
+
 FORCE_RTOL_F32 = 1e-5  # north_star: per-atom forces to 1e-5 relative in FP32
 
 
