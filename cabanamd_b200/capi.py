@@ -80,6 +80,7 @@ def load_library():
     L.cbmd_zero_force.argtypes = [vp]
     L.cbmd_force_lj.argtypes = [vp, C.c_int]
     L.cbmd_energy_lj.argtypes = [vp, C.c_int, c_dp, c_dp]
+    L.cbmd_virial_lj.argtypes = [vp, C.c_int, c_dp]
     L.cbmd_request_energy.argtypes = [vp]
     L.cbmd_comm_unique_id.argtypes = [vp]
     L.cbmd_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -288,6 +289,12 @@ class Context:
         self._ck(self.L.cbmd_energy_lj(self.h, int(self.half if half is None else half),
                                        C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def virial(self, half=None):
+        """Scalar pair virial sum r_ij . f_ij of this rank (extension; see cbmd_c_api.h)."""
+        a = C.c_double()
+        self._ck(self.L.cbmd_virial_lj(self.h, int(self.half if half is None else half), C.byref(a)))
+        return a.value
 
     # ---- Comm
     @staticmethod

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h> // header-only NVTX 3: ranges around the module entry points (option "nvtx")
 
 #include <cstdint>
 #include <cstdio>
@@ -213,6 +214,7 @@ struct cbmd_ctx
 
     // options
 
+    bool nvtx = false; // option "nvtx" / CBMD_NVTX=1: NVTX range per timed region (Force, Neigh, Comm, ...)
     // CUDA-event timers (cbmd_timing_*)
     bool timing = false;
     struct Bucket
@@ -242,10 +244,18 @@ struct TimedRegion
             cudaEventCreate( &e );
         return e;
     }
+    bool ranged = false;
     TimedRegion( cbmd_ctx *c, int bucket )
         : ctx( c )
         , b( bucket )
     {
+        if ( ctx->nvtx )
+        {
+            static const char *const names[] = { "cbmd:Force", "cbmd:Neigh", "cbmd:Comm", "cbmd:Integrate",
+                                                 "cbmd:Other", "cbmd:ForceKernel" };
+            nvtxRangePushA( names[bucket] );
+            ranged = true;
+        }
         if ( !ctx->timing )
             return;
         cudaEvent_t e0 = get( ctx );
@@ -255,6 +265,8 @@ struct TimedRegion
     }
     ~TimedRegion()
     {
+        if ( ranged )
+            nvtxRangePop();
         if ( !e1 )
             return;
         cudaEventRecord( e1, ctx->stream );

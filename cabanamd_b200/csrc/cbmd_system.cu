@@ -224,6 +224,8 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
                              std::to_string( prop.minor ) + ")" );
         cbmd_ctx *ctx = new cbmd_ctx;
         ctx->device = device;
+        if ( const char *e = getenv( "CBMD_NVTX" ) ) // NVTX ranges around the module entry points
+            ctx->nvtx = atoi( e ) != 0;
         if ( const char *e = getenv( "CBMD_OVERLAP" ) ) // A/B switch for measurements
             ctx->overlap = atoi( e );
         if ( const char *e = getenv( "CBMD_HALO_STAGES" ) ) // A/B switch: 3 = per-dimension forwarding
@@ -340,6 +342,8 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
     std::string n( name ? name : "" );
     if ( n == "overlap" )
         ctx->overlap = (int)value;
+    else if ( n == "nvtx" )
+        ctx->nvtx = value != 0.0;
     else if ( n == "halo_stages" )
     {
         // multi-rank ghost refresh: 1 = every ghost straight from its root rank in one NCCL

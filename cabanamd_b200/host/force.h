@@ -77,6 +77,14 @@ class ForceLJ : public Force<t_System, t_Neighbor>
                     "cbmd_energy_lj" );
         return pe;
     }
+    // scalar pair virial of this rank, sum r_ij . f_ij over the pairs inside the cutoff (an extension:
+    // the reference's pressure is a TODO, cabanamd_impl.h:477-480); free after energy_follows()
+    double compute_virial( t_System *s, t_Neighbor *neighbor )
+    {
+        double w = 0.0;
+        cbmd_check( cbmd_virial_lj( s->ctx, neighbor->half_neigh ? 1 : 0, &w ), "cbmd_virial_lj" );
+        return w;
+    }
     void energy_follows() override { cbmd_check( cbmd_request_energy( system->ctx ), "cbmd_request_energy" ); }
     const char *name() override { return "Force:LJCabana"; }
 

@@ -111,6 +111,13 @@ extern "C"
      * pe_corrected (may be NULL): half-list energy with fac=1 for every stored pair
      * (SURVEY Appendix B.4); equals *pe for full lists. */
     int cbmd_energy_lj( cbmd_ctx *ctx, int half, double *pe, double *pe_corrected );
+    /* Scalar pair virial W = sum over the pairs inside the force cutoff of r_ij . f_ij =
+     * rsq * fpair, each pair once (this rank's share; sum over ranks for the global value; the
+     * pressure is (N kB T + W/3) / V).  An extension: the reference has no virial (its pressure is
+     * a TODO, src/cabanamd_impl.h:477-480).  Accumulated in the same sweep as the energy
+     * (cbmd_request_energy before cbmd_force_lj makes it free), reduced in two deterministic
+     * levels; otherwise one stand-alone sweep. */
+    int cbmd_virial_lj( cbmd_ctx *ctx, int half, double *virial );
     /* One-shot hint from the step loop (cabanamd_impl.h:363-366 evaluates the energy on
      * thermo steps right after force->compute at unchanged positions): the NEXT
      * cbmd_force_lj also accumulates compute_energy in the same neighbour sweep, and
@@ -194,6 +201,9 @@ extern "C"
      *   "neigh_kernel" 0 (default) Verlet build by a warp per cell over a staged 27-cell stencil;
      *               1 = one thread per atom walking a 5x5x5 stencil of half-size cells (faster
      *               build, rows in an order the force sweep likes less).  Same sets.
+     *   "halo_stages" 1 (default) multi-rank ghost refresh straight from the root ranks in one NCCL
+     *               group; 3 = the reference's forwarding scheme, one group per dimension
+     *   "nvtx"      1 = NVTX ranges (cbmd:Force, cbmd:Neigh, cbmd:Comm, ...) around the entry points
      *   "overlap"   1 (default) halo refresh on a second stream under the interior force tiles
      * Environment overrides read at cbmd_create: CBMD_GATHER, CBMD_PRECISION, CBMD_NEIGH_KERNEL,
      * CBMD_ROW_ORDER, CBMD_HALF_KERNEL, CBMD_HALO_STAGES, CBMD_OVERLAP. */

@@ -590,6 +590,68 @@ inline double energy_full_f32( const double *x, const int *type, int n_local, co
     return PE;
 }
 
+// ---------------------------------------------------------------------------
+// Kokkos::Random_XorShift64_Pool as the reference's neighbour-list unit test draws from it
+// (unit_test/tstNeighbor.hpp:269-282: PoolType pool( 342343901 ); position(p,d) =
+// Kokkos::rand<RandomType,double>::draw( gen, box_min, box_max )).  Kokkos is an un-vendored
+// dependency (4.3.01, CMakeLists.txt): this restates the published algorithm of
+// Kokkos_Random.hpp from its documentation/source as remembered — xorshift64* with the
+// multiplier 2685821657736338717, pool states seeded from 17 warm-up draws + four 16-bit
+// slices of rand() per state — for the SERIAL backend, where the pool holds one state and
+// the parallel_for visits p = 0..n-1 in order, so the stream is defined (on OpenMP/CUDA the
+// atom <-> draw assignment depends on the thread schedule).  NOT verified against a Kokkos
+// build here; it replaces "some seeded RNG" by the reference's intended input.
+// ---------------------------------------------------------------------------
+struct KokkosXorShift64
+{
+    uint64_t state;
+    explicit KokkosXorShift64( uint64_t s )
+        : state( s == 0 ? uint64_t( 1318319 ) : s )
+    {
+    }
+    uint32_t urand()
+    {
+        state ^= state >> 12;
+        state ^= state << 25;
+        state ^= state >> 27;
+        uint64_t tmp = state * 2685821657736338717ULL;
+        tmp = tmp >> 16;
+        return static_cast<uint32_t>( tmp & 0xffffffffULL );
+    }
+    uint64_t urand64()
+    {
+        state ^= state >> 12;
+        state ^= state << 25;
+        state ^= state >> 27;
+        return ( state * 2685821657736338717ULL ) - 1;
+    }
+    int rand() { return static_cast<int>( urand() / 2 ); }
+    double drand() { return 1.0 * urand64() / static_cast<double>( 0xffffffffffffffffULL - 1 ); }
+    double drand( double start, double end ) { return drand() * ( end - start ) + start; }
+};
+
+// state 0 of Random_XorShift64_Pool( seed ) (init: 17 warm-up draws, then four rand() per state)
+inline uint64_t kokkos_pool_state0( uint64_t seed )
+{
+    if ( seed == 0 )
+        seed = uint64_t( 1318319 );
+    KokkosXorShift64 gen( seed );
+    for ( int i = 0; i < 17; i++ )
+        gen.rand();
+    const int n1 = gen.rand(), n2 = gen.rand(), n3 = gen.rand(), n4 = gen.rand();
+    return ( ( static_cast<uint64_t>( n1 ) & 0xffff ) << 00 ) | ( ( static_cast<uint64_t>( n2 ) & 0xffff ) << 16 ) |
+           ( ( static_cast<uint64_t>( n3 ) & 0xffff ) << 32 ) | ( ( static_cast<uint64_t>( n4 ) & 0xffff ) << 48 );
+}
+
+// createAtoms of tstNeighbor.hpp on the Serial backend: x[p][d] for p = 0..n-1, d = 0..2
+inline void kokkos_serial_positions( uint64_t seed, int n, double lo, double hi, double *x )
+{
+    KokkosXorShift64 gen( kokkos_pool_state0( seed ) );
+    for ( int p = 0; p < n; p++ )
+        for ( int d = 0; d < 3; d++ )
+            x[3 * p + d] = gen.drand( lo, hi );
+}
+
 // Serial on purpose: the j-side updates make the sum order matter and the
 // oracle must be deterministic.  force_lj_cabana_neigh_impl.h:205-259
 inline void force_half( const double *x, const int *type, double *f, int n_local,

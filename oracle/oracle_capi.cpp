@@ -153,6 +153,12 @@ void orc_velocity_geom( int seed, const double *coord, double *u3 )
     u3[2] = rng.uniform();
 }
 
+// createAtoms of unit_test/tstNeighbor.hpp:262-285 (Kokkos XorShift64 pool, Serial backend)
+void orc_kokkos_positions( unsigned long long seed, int n, double lo, double hi, double *x )
+{
+    kokkos_serial_positions( seed, n, lo, hi, x );
+}
+
 void orc_dims_create( int n, int *dims )
 {
     auto g = dims_create( n );

@@ -65,6 +65,7 @@ def lib():
                               C.c_int, c_ip, c_ip, c_dp, c_dp]
     L.orc_velocity_geom.argtypes = [C.c_int, c_dp, c_dp]
     L.orc_dims_create.argtypes = [C.c_int, c_ip]
+    L.orc_kokkos_positions.argtypes = [C.c_ulonglong, C.c_int, C.c_double, C.c_double, c_dp]
     L.orc_sim_new.restype = vp
     L.orc_sim_new.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_double, C.c_int,
                               C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
@@ -193,6 +194,13 @@ class NeighList:
         return self.L.orc_energy_lj(self.h, dp(x), ip(type_), self.n_local, int(half),
                                     int(corrected), nt, dp(np.ascontiguousarray(lj1)),
                                     dp(np.ascontiguousarray(lj2)), dp(np.ascontiguousarray(cutsq)))
+
+
+def kokkos_positions(seed, n, lo, hi):
+    """createAtoms of the reference's tstNeighbor (Kokkos XorShift64 pool, Serial backend)."""
+    x = np.empty((n, 3))
+    lib().orc_kokkos_positions(seed, n, lo, hi, dp(x))
+    return x
 
 
 def integrate(which, x, v, f, type_, mass, dt=0.005, mvv2e=1.0):

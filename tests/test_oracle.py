@@ -10,14 +10,31 @@ import oracle_lib as O
 
 
 def tst_neighbor_config(seed=342343901):
-    """unit_test/tstNeighbor.hpp:289-304: 1000 atoms, last 200 ghost, rc=2.32,
-    uniform in [-5.3 rc, 4.7 rc]^3 (own seeded RNG; the Kokkos XorShift pool stream
-    is not reproducible without Kokkos)."""
+    """unit_test/tstNeighbor.hpp:262-304: 1000 atoms, last 200 ghost, rc=2.32, uniform in
+    [-5.3 rc, 4.7 rc]^3 drawn from Kokkos::Random_XorShift64_Pool(342343901) — the stream of the
+    Serial backend, restated in oracle/oracle.hpp (KokkosXorShift64), so the fixture is the
+    reference test's own input."""
     rc = 2.32
     lo, hi = -5.3 * rc, 4.7 * rc
-    rng = np.random.default_rng(seed)
-    x = rng.uniform(lo, hi, size=(1000, 3))
+    x = O.kokkos_positions(seed, 1000, lo, hi)
     return x, 800, rc, lo, hi
+
+
+def test_kokkos_pool_stream_properties():
+    """The restated pool: values inside the box, well spread, deterministic, and xorshift64*'s
+    first output for a known state (state 1: 1 ^ 1<<25 ^ ... by hand)."""
+    x, _, rc, lo, hi = tst_neighbor_config()
+    assert x.shape == (1000, 3) and np.all(x >= lo) and np.all(x < hi)
+    assert np.array_equal(x, tst_neighbor_config()[0])
+    assert abs(x.mean() - 0.5 * (lo + hi)) < 0.03 * (hi - lo)
+    assert len(np.unique(x)) == x.size
+    # hand evaluation of one xorshift64* step from state 1
+    s = 1
+    s ^= s >> 12
+    s ^= (s << 25) & (2 ** 64 - 1)
+    s ^= s >> 27
+    u = ((s * 2685821657736338717) % 2 ** 64 - 1) % 2 ** 64
+    assert s == 33554433 and 0 <= u < 2 ** 64
 
 
 @pytest.mark.parametrize("half", [False, True])
