@@ -270,7 +270,28 @@ struct TimedRegion
         if ( !e1 )
             return;
         cudaEventRecord( e1, ctx->stream );
-        ctx->bucket[b].pending.push_back( e1 );
+        auto &B = ctx->bucket[b];
+        B.pending.push_back( e1 );
+        // long runs: fold the pairs that have already completed into the totals (no stall) so the
+        // number of live events stays bounded
+        if ( B.pending.size() >= 1024 )
+        {
+            size_t k = 0;
+            while ( k + 1 < B.pending.size() && cudaEventQuery( B.pending[k + 1] ) == cudaSuccess )
+            {
+                float ms = 0.f;
+                if ( cudaEventElapsedTime( &ms, B.pending[k], B.pending[k + 1] ) == cudaSuccess )
+                {
+                    B.ms += ms;
+                    B.count++;
+                }
+                ctx->event_pool.push_back( B.pending[k] );
+                ctx->event_pool.push_back( B.pending[k + 1] );
+                k += 2;
+            }
+            B.pending.erase( B.pending.begin(), B.pending.begin() + k );
+            (void)cudaGetLastError(); // a "not ready" from the last query is not an error
+        }
     }
 };
 

@@ -75,7 +75,11 @@ class System
     void init()
     {
         if ( !ctx )
+        {
             cbmd_check( cbmd_create( &ctx, World::get().device ), "cbmd_create" );
+            if ( CBMD_FORCE_PRECISION == 32 ) // FP32 build variant (types.h)
+                cbmd_check( cbmd_set_option( ctx, "precision", 32 ), "cbmd_set_option(precision)" );
+        }
     }
 
     // host mirrors only grow (system_1aosoa.h:59-67)

@@ -6,8 +6,15 @@
 #define CBMD_HOST_TYPES_H
 
 typedef int T_INT;
+// FP32 build variant (reference src/types.h:133-148, -DT_F_FLOAT=float -DT_X_FLOAT=float): built
+// with -DCBMD_SINGLE_PRECISION (make -C cabanamd_b200/host cbnMD_f32).  The pair forces are then
+// evaluated in FP32 on float positions (libcbmd_cuda option "precision" 32, k_force_full_f32);
+// the integration state on the device and the host-side arrays stay FP64, because the C ABI
+// exchanges doubles — the variant narrows the force evaluation, where the time goes.
 #ifdef CBMD_SINGLE_PRECISION
-#error "the FP32 build variant is not available yet; libcbmd_cuda computes in FP64"
+#define CBMD_FORCE_PRECISION 32
+#else
+#define CBMD_FORCE_PRECISION 64
 #endif
 typedef double T_FLOAT;
 typedef T_FLOAT T_X_FLOAT;

@@ -48,13 +48,13 @@ def built():
     assert os.path.exists(CBNMD)
 
 
-def run_cbnmd(tmp_path, deck, *args, env=None):
+def run_cbnmd(tmp_path, deck, *args, env=None, exe=None):
     f = tmp_path / "in.deck"
     f.write_text(deck)
     out, err = tmp_path / "md.out", tmp_path / "md.err"
     e = dict(os.environ)
     e.update(env or {})
-    p = subprocess.run([CBNMD, "-il", str(f), "-o", str(out), "-e", str(err), *args],
+    p = subprocess.run([exe or CBNMD, "-il", str(f), "-o", str(out), "-e", str(err), *args],
                        capture_output=True, text=True, cwd=tmp_path, env=e, timeout=600)
     return p, (out.read_text() if out.exists() else ""), (err.read_text() if err.exists() else "")
 
@@ -116,6 +116,24 @@ def parse_thermo(out):
         if m:
             rows.append((int(m.group(1)), float(m.group(2)), float(m.group(3)), float(m.group(4))))
     return rows
+
+
+@pytest.mark.gpu
+def test_cbnmd_fp32_build_variant(tmp_path):
+    """cbnMD_f32 (-DCBMD_SINGLE_PRECISION, the reference's T_F_FLOAT/T_X_FLOAT = float build): same
+    deck, thermo rows track the FP64 binary's to float accuracy and the run conserves energy."""
+    deck = DECK.format(c=10, steps=100)
+    p64, out64, err64 = run_cbnmd(tmp_path, deck)
+    d32 = tmp_path / "f32"
+    d32.mkdir()
+    p32, out32, err32 = run_cbnmd(d32, deck, exe=CBNMD + "_f32")
+    assert p64.returncode == 0 and p32.returncode == 0, p32.stderr + err32
+    r64, r32 = np.array(parse_thermo(out64)), np.array(parse_thermo(out32))
+    assert r64.shape == r32.shape and len(r32) == 11
+    assert not np.array_equal(r64, r32)                      # it is a different arithmetic
+    assert np.abs(r64[:3, 1:] - r32[:3, 1:]).max() < 5e-5    # same physics at the start
+    e32 = r32[:, 2] + r32[:, 3]
+    assert np.abs(e32 - e32[0]).max() < 1e-3                 # NVE drift stays small
 
 
 @pytest.mark.gpu
