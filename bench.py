@@ -628,6 +628,13 @@ def main():
         roofline_fp32 = roofline_of(m3, False, 32, peak, peak_src,
                                     "k_force_full_f32 (float4 LDG.128, index stream through TEX)")
         roofline_fp32["bytes_convention"] = "SURVEY 8d with 12-byte positions/forces (24 -> 12)"
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "force_traffic.json")))
+            if f"full_{args.cells}_f32" in tr:
+                roofline_fp32["traffic"] = tr[f"full_{args.cells}_f32"]
+                roofline_fp32["traffic_source"] = tr.get("source")
+        except Exception:
+            pass
         extra["FP32 force variant (precision=32), same workload"] = {
             "value": s3.N * md(m3, args.steps), "unit": UNIT, "atoms": s3.N,
             "force_kernel_ms": roofline_fp32["avg_launch_ms"], "roofline_frac": roofline_fp32["frac"]}

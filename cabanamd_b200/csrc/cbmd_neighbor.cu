@@ -65,9 +65,15 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
 #pragma unroll
     for ( int k = 0; k < K; k++ )
         c[k] = cand[k];
-    bool ok[K], amb[K], js[K];
+    bool ok[K], amb[K];
+    int val[K]; // the entry to store: index (+ NB_JSIDE)
     bool any_amb = false;
     const bool iown = i < n_local;
+    // MODE 2, per lane: an owned atom keeps x_j > x_i (i side) and owned x_j < x_i (j side), a
+    // ghost atom only the latter.  Folded into thresholds so that a candidate costs two compares:
+    // "up" can never hold for a ghost lane.
+    const float inf = __int_as_float( 0x7f800000 );
+    const float up_sure = iown ? tolx : inf, up_maybe = iown ? -tolx : inf;
 #pragma unroll
     for ( int k = 0; k < K; k++ )
     {
@@ -75,9 +81,9 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
         const float d2 = fx * fx + fy * fy + fz * fz;
         const int j = __float_as_int( c[k].w );
         const bool ns = j != i;
-        ok[k] = ns && ( d2 < r2lo );
-        amb[k] = ns && ( d2 < r2hi );
-        js[k] = false;
+        ok[k] = ns & ( d2 < r2lo );
+        amb[k] = ns & ( d2 < r2hi );
+        val[k] = j;
         if ( MODE == 1 )
         {
             // xj > xi decided in FP32 unless |xj - xi| is within its error
@@ -86,16 +92,15 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
         }
         if ( MODE == 2 )
         {
-            const bool up = fx > tolx, dn = fx < -tolx, jown = j < n_local;
-            // i side: owned i, x_j > x_i;  j side: owned j, x_j < x_i
-            const bool keep = ( iown && up ) || ( jown && dn );
-            const bool drop = ( up && !iown ) || ( dn && !jown ) || ( !iown && !jown );
-            ok[k] = ok[k] && keep;
-            amb[k] = amb[k] && !drop;
-            js[k] = dn;
+            // (bitwise on purpose: no short-circuit branches in the candidate loop)
+            const bool jown = j < n_local;
+            const bool dn = jown & ( fx < -tolx ); // surely the j side
+            ok[k] = ok[k] & ( ( fx > up_sure ) | dn );
+            amb[k] = amb[k] & ( ( fx >= up_maybe ) | ( jown & ( fx <= tolx ) ) );
+            val[k] = dn ? ( j | NB_JSIDE ) : j;
         }
-        amb[k] = amb[k] && !ok[k];
-        any_amb = any_amb || amb[k];
+        amb[k] = amb[k] & !ok[k];
+        any_amb = any_amb | amb[k];
     }
     if ( __any_sync( 0xffffffffu, any_amb ) )
     {
@@ -113,7 +118,7 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
                 {
                     const bool up = half_valid( xi, xj ), dn = half_valid( xj, xi );
                     ok[k] = ok[k] && ( ( iown && up ) || ( j < n_local && dn ) );
-                    js[k] = dn;
+                    val[k] = dn ? ( j | NB_JSIDE ) : j;
                 }
             }
     }
@@ -125,16 +130,13 @@ sweep_group( const float4 *__restrict__ cand, const XT *__restrict__ xt, const X
         const int st = ( ok[k] && count < nb_rows ) ? 1 : 0;
         const unsigned off = ( ( (unsigned)count >> 2 ) << 9 ) + ( ( (unsigned)count & 3u ) << 2 );
         char *dst = row0 + (unsigned long long)off;
-        int val = __float_as_int( c[k].w );
-        if ( MODE == 2 )
-            val |= js[k] ? NB_JSIDE : 0;
         asm volatile( "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b32 [%0], %1;\n\t}"
                       :
-                      : "l"( dst ), "r"( val ), "r"( st )
+                      : "l"( dst ), "r"( val[k] ), "r"( st )
                       : "memory" );
         count += ok[k] ? 1 : 0;
         if ( MODE == 2 )
-            count_i += ( ok[k] && !js[k] ) ? 1 : 0;
+            count_i += ( ok[k] && !( val[k] & NB_JSIDE ) ) ? 1 : 0;
     }
 }
 
