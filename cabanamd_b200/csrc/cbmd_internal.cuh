@@ -156,7 +156,7 @@ struct cbmd_ctx
     int *nb = nullptr;
     size_t nb_alloc = 0;
     int row_order = 0;         // option "row_order": 1 = bank-aware (Latin) order of full-list rows, 0 = index order
-    int neigh_kernel = 0;      // option "neigh_kernel": 0 = staged 27-cell stencil, 1 = per-thread walk over half-size cells
+    int neigh_kernel = 2;      // option "neigh_kernel": 2 = per-thread walk, cells >= r (default); 1 = walk over half-size cells; 0 = staged stencil
     float4 *cpos = nullptr;    // candidates packed in cell order for the walk kernel
     int cpos_cap = 0;
     int *nb_count = nullptr; // [cap] entries per row

@@ -348,28 +348,32 @@ __global__ void __launch_bounds__( NB_THREADS )
 }
 
 // ---------------------------------------------------------------------------
-// k_neigh_build_walk (option "neigh_kernel" 1, the default): one THREAD per owned atom walks
-// its own stencil on a grid of HALF-size cells (cell >= r/2, 5x5x5 stencil).
+// k_neigh_build_walk (option "neigh_kernel" 2, the default, and 1): one THREAD per atom walks its
+// own cell stencil.
 //
-// k_neigh_build shares one staged 27-cell stencil (cells >= r) between the lanes of a warp,
-// so every lane tests every candidate of the shared stencil: ~500-800 FP32 tests per atom
-// for ~78 accepted, and the kernel is bound by instruction issue (profiles/).  The volume of
-// a 5x5x5 stencil of half-size cells is 2.7 x smaller, and a thread that walks its OWN stencil
-// tests only its own ~300 candidates.  The 25 (x,y) columns of a stencil are 25 runs that are
-// contiguous in cell order; the candidates are packed once per build in that order as 16-byte
-// records {x,y,z relative to the box centre as FP32, atom index} (k_pack_candidates), so a
-// thread streams each run with LDG.128 and the 32 neighbouring atoms of a warp hit the same
-// lines in L1.  The decision is k_neigh_build's: FP32 with an explicit error bound (M = the
-// largest relative coordinate, measured while packing), exact FP64 re-evaluation of the
-// reference criterion from the 32-byte records for the few ambiguous candidates — the SET is
-// bit-identical to the oracle's.  Rows come out in ascending (half-cell, index) order.
+// k_neigh_build (option 0, round 1) gives a warp one cell and shares a staged 27-cell stencil
+// between the cell's atoms: ~19 of 32 lanes have an atom, and every lane pays the address
+// arithmetic of an append for every candidate — 2.74 G warp instructions per build at 4 M atoms,
+// 85 % issue-bound (profiles/r2_neigh_kernels.txt).  Here a warp is 32 consecutive atoms (all
+// lanes busy; in the MD loop they are neighbours in space because the atoms are cell-sorted),
+// each thread streams the runs of ITS stencil — the columns of the cell grid are contiguous in
+// cell order, and the candidates are packed once per build in that order as 16-byte records
+// {x,y,z relative to the box centre as FP32, atom index} (k_pack_candidates), so a run is a
+// sequence of LDG.128 that the lanes of a warp share in L1 — and works in two phases per 32
+// candidates: DECIDE (FP32 test, one bit per candidate, no stores; fully unrolled) and APPEND
+// (only the accepted ones, ~1 in 7).  The decision is k_neigh_build's: FP32 with an explicit
+// error bound (M = the largest relative coordinate, measured while packing), exact FP64
+// re-evaluation of the reference criterion from the 32-byte records for the few ambiguous
+// candidates — the SET is bit-identical to the oracle's.
 //
-// Measured on B200, 4 M atoms (profiles/r2_neigh_kernels.txt): 2.0 ms + 0.3 ms for the finer
-// cell lists and the packing, against 2.85 ms for k_neigh_build — half the instructions.  But
-// the force sweep that follows is 4 % SLOWER on rows in half-cell order (0.717 ms against
-// 0.687 ms on k_neigh_build's rows, which ascend in atom index because the atoms are sorted
-// by the cells it walks): 20 sweeps lose more than one build gains, so the MD loop keeps
-// k_neigh_build (option "neigh_kernel" 0, the default) and this kernel is the A/B leg.
+// reach 1 (option 2): cells >= r, 3x3x3 stencil, 9 runs of ~58 candidates.  Rows ascend in atom
+// index like k_neigh_build's (the atoms are sorted by these very cells), which is the order the
+// force sweep is fastest on.  Measured on B200, 4 M atoms: build 3.2 -> 2.7 ms, force sweep
+// unchanged, 3.82e9 -> 3.93e9 atom-steps/s.
+// reach 2 (option 1): cells >= r/2, 5x5x5 stencil, 25 runs of ~12: 40 % fewer candidates and the
+// fastest build (2.0 ms + 0.3 ms for the finer cell lists), but its rows come out in half-cell
+// order and the force sweep is 4 % slower on them (0.717 against 0.687 ms) — 20 sweeps lose more
+// than one build gains, so it is only the A/B leg.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__( 256 )
     k_pack_candidates( const XT *__restrict__ xt, const int *__restrict__ cell_atoms, int n_total,
@@ -392,17 +396,19 @@ __global__ void __launch_bounds__( 256 )
         atomicMax( mag_bits, __float_as_int( mag ) ); // non-negative floats order like ints
 }
 
-template <bool HALF>
+// MODE as in sweep_group: 0 full, 1 half, 2 PULL rows (rows for ghost atoms too, n_rows = all atoms)
+template <int MODE>
 __global__ void __launch_bounds__( 128 )
-    k_neigh_build_walk( const XT *__restrict__ xt, int n_local, GridDesc g,
+    k_neigh_build_walk( const XT *__restrict__ xt, int n_local, int n_rows, GridDesc g,
                         const int *__restrict__ cell_start, const float4 *__restrict__ cpos,
                         const int *__restrict__ atom_cell, double3 origin, double rsqr,
                         const int *__restrict__ mag_bits, int *__restrict__ nb, int nb_rows,
-                        int *__restrict__ nb_count, int *__restrict__ d_max, int zr_cells )
+                        int *__restrict__ nb_count, int *__restrict__ d_max, int reach,
+                        int *__restrict__ nb_count_i )
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int count = 0;
-    if ( i < n_local )
+    int count = 0, count_i = 0;
+    if ( i < n_rows )
     {
         // FP32 error of d2: relative coordinates carry <= 2^-24*M each, so |fx - dx| <= 1.2e-7*M
         // and, with three more roundings in the sum, |d2f - d2| <= (8.4e-7*M + 1.8e-7)*(1 + d2);
@@ -415,77 +421,121 @@ __global__ void __launch_bounds__( 128 )
         const float tolx = 1.0e-5f * fmaxf( 1.0f, M );
         const XT xi = ld_xt( xt + i );
         const float xr = (float)( xi.x - origin.x ), yr = (float)( xi.y - origin.y ), zr = (float)( xi.z - origin.z );
+        // PULL rows: an owned atom keeps x_j > x_i (i side) and owned x_j < x_i (j side, flagged),
+        // a ghost atom only the latter; folded into thresholds ("up" never holds for a ghost)
+        const bool iown = i < n_local;
+        const float inf = __int_as_float( 0x7f800000 );
+        const float up_sure = iown ? tolx : inf, up_maybe = iown ? -tolx : inf;
         const int c = atom_cell[i];
         const int nz = g.n[2], ny = g.n[1], nx = g.n[0];
         const int cz = c % nz, cy = ( c / nz ) % ny, cx = c / ( nz * ny );
-        const int zlo = max( cz - zr_cells, 0 ), zhi = min( cz + zr_cells, nz - 1 );
-        const int alo = max( cx - 2, 0 ), ahi = min( cx + 2, nx - 1 );
-        const int blo = max( cy - 2, 0 ), bhi = min( cy + 2, ny - 1 );
+        const int zlo = max( cz - reach, 0 ), zhi = min( cz + reach, nz - 1 );
+        const int alo = max( cx - reach, 0 ), ahi = min( cx + reach, nx - 1 );
+        const int blo = max( cy - reach, 0 ), bhi = min( cy + reach, ny - 1 );
         char *const row0 = (char *)( nb + nb_tile_base( i, nb_rows ) );
         for ( int a = alo; a <= ahi; a++ )
             for ( int b = blo; b <= bhi; b++ )
             {
                 const int row = ( a * ny + b ) * nz;
                 const int s0 = __ldg( cell_start + row + zlo ), s1 = __ldg( cell_start + row + zhi + 1 );
-                // the run in chunks of 32 candidates: first DECIDE (one bit per candidate, a short
-                // loop without stores), then APPEND the accepted ones (~1 in 4) — the address
-                // arithmetic of an append is not paid for the rejected candidates
+                // the run in chunks of 32 candidates: first DECIDE (one bit per candidate, no
+                // stores), then APPEND the accepted ones — the address arithmetic of an append is
+                // not paid for the rejected candidates.  sure / amb: surely accepted / to be
+                // decided exactly; js: accepted entries that are the j side of their pair (PULL).
                 for ( int c0 = s0; c0 < s1; c0 += 32 )
                 {
-                    const int c1 = min( c0 + 32, s1 );
-                    unsigned sure = 0u, amb = 0u;
-#pragma unroll 4
-                    for ( int s = c0; s < c1; s++ )
+                    const int rem = min( 32, s1 - c0 );
+                    const float4 *cp = cpos + c0;
+                    unsigned sure = 0u, amb = 0u, js = 0u;
+#define CBMD_DECIDE( K )                                                                          \
+    {                                                                                             \
+        const float4 q = __ldg( cp + ( K ) );                                                     \
+        const float fx = q.x - xr, fy = q.y - yr, fz = q.z - zr;                                  \
+        const float d2 = fx * fx + fy * fy + fz * fz;                                             \
+        bool in_lo = d2 < r2lo, in_hi = d2 < r2hi;                                                \
+        if ( MODE == 1 )                                                                          \
+        { /* xj > xi decided in FP32 unless |xj - xi| is within its error */                      \
+            in_lo = in_lo & ( fx > tolx );                                                        \
+            in_hi = in_hi & ( fx >= -tolx );                                                      \
+        }                                                                                         \
+        if ( MODE == 2 )                                                                          \
+        {                                                                                         \
+            const bool jown = __float_as_int( q.w ) < n_local;                                    \
+            const bool dn = jown & ( fx < -tolx );                                                \
+            in_lo = in_lo & ( ( fx > up_sure ) | dn );                                            \
+            in_hi = in_hi & ( ( fx >= up_maybe ) | ( jown & ( fx <= tolx ) ) );                   \
+            js |= dn ? ( 1u << ( K ) ) : 0u;                                                      \
+        }                                                                                         \
+        sure |= in_lo ? ( 1u << ( K ) ) : 0u;                                                     \
+        amb |= in_hi ? ( 1u << ( K ) ) : 0u;                                                      \
+    }
+                    if ( rem == 32 )
                     {
-                        const float4 q = __ldg( cpos + s );
-                        const float fx = q.x - xr, fy = q.y - yr, fz = q.z - zr;
-                        const float d2 = fx * fx + fy * fy + fz * fz;
-                        bool in_lo = d2 < r2lo, in_hi = d2 < r2hi;
-                        if ( HALF )
-                        { // xj > xi decided in FP32 unless |xj - xi| is within its error
-                            in_lo = in_lo && fx > tolx;
-                            in_hi = in_hi && fx >= -tolx;
-                        }
-                        const unsigned bit = 1u << ( s - c0 );
-                        sure |= in_lo ? bit : 0u;
-                        amb |= in_hi ? bit : 0u;
+#pragma unroll
+                        for ( int k = 0; k < 32; k++ ) // fully unrolled: the bits are immediates
+                            CBMD_DECIDE( k )
                     }
+                    else
+                    {
+#pragma unroll 1
+                        for ( int k = 0; k < rem; k++ )
+                            CBMD_DECIDE( k )
+                    }
+#undef CBMD_DECIDE
                     amb &= ~sure;
                     while ( amb )
                     { // exact re-evaluation of the reference criterion (rare)
                         const int k = __ffs( amb ) - 1;
                         amb &= amb - 1u;
-                        const int j = __float_as_int( __ldg( cpos + c0 + k ).w );
+                        const int j = __float_as_int( __ldg( cp + k ).w );
                         const XT xj = ld_xt( xt + j );
                         bool ok = dist2_exact( __dsub_rn( xi.x, xj.x ), __dsub_rn( xi.y, xj.y ), __dsub_rn( xi.z, xj.z ) ) <= rsqr;
-                        if ( HALF )
+                        if ( MODE == 1 )
                             ok = ok && half_valid( xi, xj );
+                        if ( MODE == 2 )
+                        {
+                            const bool up = half_valid( xi, xj ), dn = half_valid( xj, xi );
+                            ok = ok && ( ( iown && up ) || ( j < n_local && dn ) );
+                            js = dn ? ( js | ( 1u << k ) ) : ( js & ~( 1u << k ) );
+                        }
                         sure |= ok ? ( 1u << k ) : 0u;
                     }
                     while ( sure )
                     {
                         const int k = __ffs( sure ) - 1;
                         sure &= sure - 1u;
-                        const int j = __float_as_int( __ldg( &cpos[c0 + k].w ) );
+                        const int j = __float_as_int( __ldg( &cp[k].w ) );
                         if ( j != i ) // the atom itself passes the distance test
                         {
+                            const bool jside = MODE == 2 && ( ( js >> k ) & 1u );
                             if ( count < nb_rows )
-                                *(int *)( row0 + ( ( (unsigned)count >> 2 ) << 9 ) + ( ( (unsigned)count & 3u ) << 2 ) ) = j;
+                                *(int *)( row0 + ( ( (unsigned)count >> 2 ) << 9 ) + ( ( (unsigned)count & 3u ) << 2 ) ) =
+                                    jside ? ( j | NB_JSIDE ) : j;
                             count++;
+                            count_i += jside ? 0 : 1;
                         }
                     }
                 }
             }
         nb_count[i] = count;
+        if ( MODE == 2 )
+            nb_count_i[i] = count_i;
         // pad the row to a multiple of four with the atom itself (never a neighbour)
         for ( int k = count; k < min( ( count + 3 ) & ~3, nb_rows ); k++ )
             *(int *)( row0 + ( ( (unsigned)k >> 2 ) << 9 ) + ( ( (unsigned)k & 3u ) << 2 ) ) = i;
     }
-    int mx = count;
+    int mx = count, mi = count_i;
     for ( int o = 16; o > 0; o >>= 1 )
+    {
         mx = max( mx, __shfl_xor_sync( 0xffffffffu, mx, o ) );
+        mi = max( mi, __shfl_xor_sync( 0xffffffffu, mi, o ) );
+    }
     if ( ( threadIdx.x & 31 ) == 0 && mx > 0 )
+    {
         atomicMax( d_max, mx );
+        if ( MODE == 2 )
+            atomicMax( d_max + 1, mi ); // longest reference row (without the j-side entries)
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -741,18 +791,20 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
 
     // cell grid of size >= rcut around the owned box; atoms outside are clamped into
     // the edge cells, which keeps |cell(i)-cell(j)| <= 1 for every pair within rcut.
-    // option "neigh_kernel" 0 (default): cells >= rcut, one halo layer, staged 27-cell stencil;
-    // 1: cells >= rcut/2, two halo layers, 5x5x5 stencil walked by one thread per atom
+    // option "neigh_kernel" 2 (default): cells >= rcut, one halo layer, 3x3x3 stencil walked by one
+    // thread per atom; 1: cells >= rcut/2, two halo layers, 5x5x5 stencil, same kernel; 0: warp
+    // per cell over a staged 27-cell stencil (round 1)
     // half lists for the atomics-free Newton-3 sweep get PULL rows (sweep_group MODE 2): rows for
     // owned and ghost atoms, built by the staged kernel
     const bool pull = half && ctx->half_kernel == 1;
-    const bool walk = ctx->neigh_kernel == 1 && !pull;
-    const double cell = walk ? 0.5 * rcut : rcut;
+    const bool walk = ctx->neigh_kernel >= 1;
+    const bool walk_half = ctx->neigh_kernel == 1; // 1: half-size cells, 5x5x5; 2: cells >= rcut, 3x3x3
+    const double cell = ( walk && walk_half ) ? 0.5 * rcut : rcut;
     const double din[3] = { cell, cell, cell };
     int nbin[3];
     double gmin[3], gmax[3];
     GridDesc g;
-    cbmd_binning_grid( ctx, din, walk ? 2 : 1, nbin, gmin, gmax, g );
+    cbmd_binning_grid( ctx, din, ( walk && walk_half ) ? 2 : 1, nbin, gmin, gmax, g );
     for ( int d = 0; d < 3; d++ )
         if ( 1.0 / g.rdx[d] < din[d] )
         {
@@ -839,14 +891,18 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
         CBMD_CUDA( cudaMemsetAsync( d_max, 0, 2 * sizeof( int ), s ) );
         if ( n_local > 0 && walk )
         {
-            if ( half )
-                k_neigh_build_walk<true><<<div_up( n_local, 128 ), 128, 0, s>>>(
-                    ctx->xt, n_local, g, ctx->cell_start, ctx->cpos, ctx->atom_cell, centre, rsqr, d_mag, ctx->nb,
-                    rows, ctx->nb_count, d_max, 2 );
+            const int n_rows = pull ? n_total : n_local, reach = walk_half ? 2 : 1;
+#define NBW_LAUNCH( MODE )                                                                        \
+    k_neigh_build_walk<MODE><<<div_up( n_rows, 128 ), 128, 0, s>>>(                               \
+        ctx->xt, n_local, n_rows, g, ctx->cell_start, ctx->cpos, ctx->atom_cell, centre, rsqr, d_mag, ctx->nb, rows, \
+        ctx->nb_count, d_max, reach, ctx->nb_count_i )
+            if ( pull )
+                NBW_LAUNCH( 2 );
+            else if ( half )
+                NBW_LAUNCH( 1 );
             else
-                k_neigh_build_walk<false><<<div_up( n_local, 128 ), 128, 0, s>>>(
-                    ctx->xt, n_local, g, ctx->cell_start, ctx->cpos, ctx->atom_cell, centre, rsqr, d_mag, ctx->nb,
-                    rows, ctx->nb_count, d_max, 2 );
+                NBW_LAUNCH( 0 );
+#undef NBW_LAUNCH
             CBMD_LAUNCH_CHECK( ctx );
         }
         else if ( n_local > 0 )

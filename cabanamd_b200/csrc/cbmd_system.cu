@@ -237,7 +237,7 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
         if ( const char *e = getenv( "CBMD_ROW_ORDER" ) ) // A/B switch: 1 = bank-aware row order
             ctx->row_order = atoi( e ) == 1 ? 1 : 0;
         if ( const char *e = getenv( "CBMD_NEIGH_KERNEL" ) ) // A/B switch: 1 = per-thread walk, half-size cells
-            ctx->neigh_kernel = atoi( e ) == 1 ? 1 : 0;
+            ctx->neigh_kernel = ( atoi( e ) >= 0 && atoi( e ) <= 2 ) ? atoi( e ) : 2;
         if ( const char *e = getenv( "CBMD_PRECISION" ) ) // 32 = FP32 pair arithmetic (full lists)
             ctx->precision = atoi( e ) == 32 ? 32 : 64;
         CBMD_CUDA( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
@@ -376,10 +376,11 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
     }
     else if ( n == "neigh_kernel" )
     {
-        // Verlet build: 0 = warp per cell over a staged 27-cell stencil (default); 1 = one thread
-        // per atom walks a 5x5x5 stencil of half-size cells.  Same sets, bit for bit.
-        if ( (int)value != 0 && (int)value != 1 )
-            throw CbmdError( "neigh_kernel must be 0 or 1" );
+        // Verlet build: 2 = one thread per atom walks its 3x3x3 stencil of cells >= r (default);
+        // 1 = the same over a 5x5x5 stencil of half-size cells; 0 = warp per cell over a staged
+        // 27-cell stencil.  Same sets, bit for bit.
+        if ( (int)value < 0 || (int)value > 2 )
+            throw CbmdError( "neigh_kernel must be 0, 1 or 2" );
         ctx->neigh_kernel = (int)value;
     }
     else if ( n == "precision" )

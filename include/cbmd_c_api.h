@@ -198,9 +198,10 @@ extern "C"
      *               after the build in a bank-aware (Latin) order: the eight lanes of an LDG.128
      *               group gather from eight different 16-byte positions (faster sweeps, but the
      *               re-ordering pass costs more than 20 sweeps gain).  Same sets.
-     *   "neigh_kernel" 0 (default) Verlet build by a warp per cell over a staged 27-cell stencil;
-     *               1 = one thread per atom walking a 5x5x5 stencil of half-size cells (faster
-     *               build, rows in an order the force sweep likes less).  Same sets.
+     *   "neigh_kernel" 2 (default) Verlet build by one thread per atom walking its 3x3x3 cell stencil;
+     *               1 = the same over a 5x5x5 stencil of half-size cells (fastest build, rows in an
+     *               order the force sweep likes less); 0 = warp per cell over a staged stencil
+     *               (round 1).  Same sets.
      *   "halo_stages" 1 (default) multi-rank ghost refresh straight from the root ranks in one NCCL
      *               group; 3 = the reference's forwarding scheme, one group per dimension
      *   "nvtx"      1 = NVTX ranges (cbmd:Force, cbmd:Neigh, cbmd:Comm, ...) around the entry points

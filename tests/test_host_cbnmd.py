@@ -132,7 +132,7 @@ def test_cbnmd_fp32_build_variant(tmp_path):
     assert r64.shape == r32.shape and len(r32) == 11
     assert not np.array_equal(r64, r32)                      # it is a different arithmetic
     assert np.abs(r64[:3, 1:] - r32[:3, 1:]).max() < 5e-5    # same physics at the start
-    e32 = r32[:, 2] + r32[:, 3]
+    e32 = r32[:, 3]                                          # the thermo columns are T, PE, ETot
     assert np.abs(e32 - e32[0]).max() < 1e-3                 # NVE drift stays small
 
 
