@@ -469,11 +469,17 @@ __global__ void __launch_bounds__( 128 )
         sure |= in_lo ? ( 1u << ( K ) ) : 0u;                                                     \
         amb |= in_hi ? ( 1u << ( K ) ) : 0u;                                                      \
     }
-                    if ( rem == 32 )
+                    if ( rem >= 12 )
                     {
+                        // fully unrolled (the bits are immediates).  A short chunk is decided as a
+                        // whole one and the bits past its end are dropped: what lies there are the
+                        // next cells' candidates (cpos has slack behind the last atom)
 #pragma unroll
-                        for ( int k = 0; k < 32; k++ ) // fully unrolled: the bits are immediates
+                        for ( int k = 0; k < 32; k++ )
                             CBMD_DECIDE( k )
+                        const unsigned live = rem == 32 ? 0xffffffffu : ( ( 1u << rem ) - 1u );
+                        sure &= live;
+                        amb &= live;
                     }
                     else
                     {
@@ -847,7 +853,9 @@ extern "C" int cbmd_neigh_build( cbmd_ctx *ctx, double rcut, int half, int layou
                 CBMD_CUDA( cudaFree( ctx->cpos ) );
             }
             ctx->cpos = nullptr;
-            CBMD_CUDA( cudaMalloc( &ctx->cpos, (size_t)ctx->cap * sizeof( float4 ) ) );
+            // + 32 records of slack: the decide phase may read (and ignore) a whole chunk past the end
+            CBMD_CUDA( cudaMalloc( &ctx->cpos, ( (size_t)ctx->cap + 32 ) * sizeof( float4 ) ) );
+            CBMD_CUDA( cudaMemsetAsync( ctx->cpos, 0, ( (size_t)ctx->cap + 32 ) * sizeof( float4 ), s ) );
             ctx->cpos_cap = ctx->cap;
         }
         CBMD_CUDA( cudaMemsetAsync( d_mag, 0, sizeof( int ), s ) );
