@@ -691,12 +691,18 @@ inline void force_half( const double *x, const int *type, double *f, int n_local
 inline double energy( const double *x, const int *type, int n_local, const NeighList &L,
                       const Params &p, bool half, bool corrected = false )
 {
+    // The reduction order is not part of the reference (Kokkos parallel_reduce).  Each atom's
+    // terms are summed first and the per-atom sums added up: on a (nearly) perfect lattice every
+    // atom contributes the same few hundred term values, and feeding tens of millions of them
+    // one by one into a single running sum lets their rounding errors add up coherently
+    // (~1e-9 relative at 1 M atoms with rc = 5 sigma) instead of cancelling.
     double PE = 0.0;
 #pragma omp parallel for schedule( static ) reduction( + : PE )
     for ( int i = 0; i < n_local; i++ )
     {
         const double xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
         const int ti = type[i];
+        double pe_i = 0.0;
         for ( int64_t k = L.offsets[i]; k < L.offsets[i + 1]; k++ )
         {
             const int j = L.neigh[k];
@@ -712,12 +718,13 @@ inline double energy( const double *x, const int *type, int n_local, const Neigh
                 double fac = 0.5;
                 if ( half )
                     fac = ( j < n_local || corrected ) ? 1.0 : 0.5;
-                PE += fac * r6inv * ( 0.5 * lj1 * r6inv - lj2 ) / 6.0;
+                pe_i += fac * r6inv * ( 0.5 * lj1 * r6inv - lj2 ) / 6.0;
                 const double r2invc = 1.0 / cutsq;
                 const double r6invc = r2invc * r2invc * r2invc;
-                PE -= fac * r6invc * ( 0.5 * lj1 * r6invc - lj2 ) / 6.0;
+                pe_i -= fac * r6invc * ( 0.5 * lj1 * r6invc - lj2 ) / 6.0;
             }
         }
+        PE += pe_i;
     }
     return PE;
 }

@@ -235,9 +235,12 @@ class Sim:
 
     def __init__(self, ntypes=1, mass=(2.0,), eps=1.0, sigma=1.0, cut=2.5, skin=0.3, half=False,
                  exchange_rate=20, ghost_cutoff=20.0, dt=0.005, mvv2e=1.0, boltz=1.0,
-                 force_cutoff=None):
+                 force_cutoff=None, tables=None):
         self.L = lib()
-        lj1, lj2, cutsq = lj_tables(ntypes, eps, sigma, cut)
+        if tables is not None:  # explicit per-type-pair lj1, lj2, cutsq (multi-type decks)
+            lj1, lj2, cutsq = (np.ascontiguousarray(t, dtype=np.float64) for t in tables)
+        else:
+            lj1, lj2, cutsq = lj_tables(ntypes, eps, sigma, cut)
         self.tables = (lj1, lj2, cutsq)
         mass = np.ascontiguousarray(mass, dtype=np.float64)
         fc = cut if force_cutoff is None else force_cutoff

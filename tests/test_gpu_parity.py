@@ -28,6 +28,16 @@ def tst_neighbor_config(seed=342343901):
     return x, 800, rc, lo, hi
 
 
+def csr_sorted(counts, offsets, neigh, n_rows):
+    """All rows of a CSR list, each sorted: one flat array (vectorised; for whole-list equality)."""
+    c = np.asarray(counts[:n_rows], dtype=np.int64)
+    tot = int(offsets[n_rows])
+    rid = np.repeat(np.arange(n_rows, dtype=np.int64), c)
+    key = rid * (1 << 31) + np.asarray(neigh[:tot], dtype=np.int64)
+    key.sort()
+    return key
+
+
 def gpu_rows(ctx):
     counts, offsets, neigh = ctx.neigh_get()
     nl, _ = ctx.counts()
@@ -692,14 +702,73 @@ def test_long_cutoff_variant_matches_oracle(cb):
     c, o, n = sim.ctx.neigh_get()
     oc, oo, on = s0.list()
     assert np.array_equal(c, oc) and c[: len(oo) - 1].mean() > 500
-    for i in range(0, len(oo) - 1, 5):
-        assert np.array_equal(np.sort(n[o[i]:o[i + 1]]), np.sort(on[oo[i]:oo[i + 1]]))
+    nl = len(oo) - 1
+    assert np.array_equal(csr_sorted(c, o, n, nl), csr_sorted(oc, oo, on, nl))   # every row
     s0.record_thermo()
     sim.record_thermo()
     s0.run(40, 10)
     sim.run(40, 10)
     assert np.abs(np.array(sim.thermo) - np.array(s0.thermo())).max() < 1e-9
     a, b = sim.ctx.get_atoms(), s0.get()
+    fa = a["f"][: a["n_local"]][np.argsort(a["id"][: a["n_local"]])]
+    fb = b["f"][: b["n_local"]][np.argsort(b["id"][: b["n_local"]])]
+    assert np.abs(fa - fb).max() <= 1e-9 * np.abs(fb).max()
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_config1_one_million_atoms_vs_oracle(cb, half):
+    """BASELINE configs[1] at its full size (fcc 63^3 = 1 000 188 atoms, rc 2.5, skin 0.3), full and
+    half list: every neighbour row equal to the oracle's, forces 1e-10, thermo after a list period
+    (one rebuild) to round-off."""
+    from cabanamd_b200.harness import Simulation
+
+    s0 = O.Sim(mass=[2.0], half=half).create_lattice_fcc(cells=(63, 63, 63))
+    d, dom = s0.get(), s0.domain()
+    s0.setup()
+    sim = Simulation(half=half)
+    sim.set_box(dom["llo"], dom["lhi"])
+    sim.set_atoms(d["x"], d["v"], d["type"], d["id"])
+    sim.setup()
+    c, o, n = sim.ctx.neigh_get()
+    oc, oo, on = s0.list()
+    nl = len(oo) - 1
+    assert nl == 1000188 and np.array_equal(c, oc)
+    assert np.array_equal(csr_sorted(c, o, n, nl), csr_sorted(oc, oo, on, nl))
+    s0.record_thermo()
+    sim.record_thermo()
+    s0.run(25, 5)
+    sim.run(25, 5)
+    assert np.abs(np.array(sim.thermo) - np.array(s0.thermo())).max() < 1e-9
+    a, b = sim.ctx.get_atoms(fields="fi"), s0.get()
+    fa = a["f"][: a["n_local"]][np.argsort(a["id"][: a["n_local"]])]
+    fb = b["f"][: b["n_local"]][np.argsort(b["id"][: b["n_local"]])]
+    assert np.abs(fa - fb).max() <= 1e-9 * np.abs(fb).max()
+
+
+def test_config4_one_million_atoms_long_cutoff_vs_oracle(cb):
+    """BASELINE configs[4] at its full size (1 000 188 atoms, rc 5.0, ~530 stored neighbours per
+    atom): row lengths of every atom, every 97th row as a set, forces 1e-10 and thermo."""
+    from cabanamd_b200.harness import Simulation
+
+    s0 = O.Sim(mass=[2.0], cut=5.0).create_lattice_fcc(cells=(63, 63, 63))
+    d, dom = s0.get(), s0.domain()
+    s0.setup()
+    sim = Simulation(cut=5.0, max_neigh_guess=600)
+    sim.set_box(dom["llo"], dom["lhi"])
+    sim.set_atoms(d["x"], d["v"], d["type"], d["id"])
+    sim.setup()
+    c, o, n = sim.ctx.neigh_get()
+    oc, oo, on = s0.list()
+    nl = len(oo) - 1
+    assert np.array_equal(c, oc) and c[:nl].mean() > 500
+    for i in range(0, nl, 97):
+        assert np.array_equal(np.sort(n[o[i]:o[i + 1]]), np.sort(on[oo[i]:oo[i + 1]]))
+    s0.record_thermo()
+    sim.record_thermo()
+    s0.run(5, 5)
+    sim.run(5, 5)
+    assert np.abs(np.array(sim.thermo) - np.array(s0.thermo())).max() < 1e-9
+    a, b = sim.ctx.get_atoms(fields="fi"), s0.get()
     fa = a["f"][: a["n_local"]][np.argsort(a["id"][: a["n_local"]])]
     fb = b["f"][: b["n_local"]][np.argsort(b["id"][: b["n_local"]])]
     assert np.abs(fa - fb).max() <= 1e-9 * np.abs(fb).max()

@@ -224,7 +224,13 @@ def test_multi_region_multi_type_deck(tmp_path):
     """Decks of the shape of input/in.lb: overlapping regions with their own types, masses,
     velocity seeds and a full pair_coeff matrix run through the same kernels
     (inputFile_impl.h:241-303,396-410; force_lj_cabana_neigh_impl.h:70-85,178-183)."""
-    p, out, err = run_cbnmd(tmp_path, MULTI_REGION_DECK)
+    import struct
+
+    import oracle_lib as O
+
+    ref_dir = tmp_path / "ref"
+    ref_dir.mkdir()
+    p, out, err = run_cbnmd(tmp_path, MULTI_REGION_DECK, "--dumpbinary", "60", str(ref_dir))
     assert p.returncode == 0, p.stderr + err
     assert "Atoms: 2048 2048" in out
     rows = np.array(parse_thermo(out))
@@ -233,6 +239,41 @@ def test_multi_region_multi_type_deck(tmp_path):
     # NVE: total energy per atom conserved to the integrator's accuracy while T and PE move
     assert np.abs(rows[:, 3] - rows[0, 3]).max() < 5e-3
     assert np.abs(rows[:, 2] - rows[0, 2]).max() > 0.05
+
+    # ---- against the oracle: the deck's initial state (binary dump of step 0) through the oracle's
+    # step loop with the deck's masses and pair table; thermo rows and the final forces must agree
+    def read_dump(path):
+        b = path.read_bytes()
+        n = struct.unpack_from("i", b)[0]
+        off, d = 4, {}
+        for name, dt, cnt in [("id", "i4", n), ("type", "i4", n), ("q", "f8", n), ("x", "f8", 3 * n),
+                              ("v", "f8", 3 * n), ("f", "f8", 3 * n)]:
+            d[name] = np.frombuffer(b, dtype=dt, count=cnt, offset=off)
+            off += d[name].nbytes
+        return n, d
+
+    n0, d0 = read_dump(ref_dir / "output.0000000000.000")
+    n1, d1 = read_dump(ref_dir / "output.0000000060.000")
+    assert n0 == n1 == 2048 and set(np.unique(d0["type"])) == {0, 1, 2}
+    eps = np.array([[1.0, 0.9, 1.1], [0.9, 0.8, 1.0], [1.1, 1.0, 1.2]])
+    sig = np.array([[1.0, 1.05, 0.95], [1.05, 1.1, 1.0], [0.95, 1.0, 0.9]])
+    cut = np.array([[2.5, 2.5, 2.4], [2.5, 2.5, 2.5], [2.4, 2.5, 2.3]])
+    tables = (48.0 * eps * sig ** 12, 24.0 * eps * sig ** 6, cut * cut)
+    a = (4.0 / 0.8442) ** (1.0 / 3.0)
+    ref = O.Sim(ntypes=3, mass=[2.0, 3.5, 1.25], cut=2.5, skin=0.3, tables=tables)
+    ref.set_atoms([0.0] * 3, [8 * a] * 3, 1, d0["x"].reshape(-1, 3), d0["v"].reshape(-1, 3), d0["type"], d0["id"])
+    ref.setup()
+    ref.record_thermo()
+    ref.run(60, 10)
+    to = np.array(ref.thermo())
+    # printed columns: step, T, PE, ETot (6 decimals)
+    mine = rows[:, 1:4]
+    theirs = np.stack([to[:, 1], to[:, 2], to[:, 2] + to[:, 3]], axis=1)
+    assert np.abs(mine - theirs).max() < 2e-6
+    b = ref.get()
+    fo = b["f"][: b["n_local"]][np.argsort(b["id"][: b["n_local"]])]
+    fm = d1["f"].reshape(-1, 3)[np.argsort(d1["id"])]
+    assert np.abs(fm - fo).max() <= 1e-9 * np.abs(fo).max()
     # the same deck twice gives the same trace (deterministic full-list path, same rand() stream)
     p2, out2, _ = run_cbnmd(tmp_path, MULTI_REGION_DECK)
     assert [r[:4] for r in parse_thermo(out2)] == [tuple(r) for r in rows.tolist()]
