@@ -172,6 +172,60 @@ def build_sim(args, cells_per_gpu, half, nranks, rank, uid, device, temp=1.4, se
     return sim
 
 
+IN_LJ = """# 3d Lennard-Jones melt (the reference's input/in.lj with the box size and run length substituted)
+units           lj
+atom_style      atomic
+newton          off
+lattice         fcc 0.8442
+region          box block 0 {c} 0 {c} 0 {c}
+create_box      1 box
+create_atoms    1 box
+mass            1 2.0
+velocity        all create 1.4 87287 loop geom
+pair_style      lj/cut 2.5
+pair_coeff      1 1 1.0 1.0 2.5
+neighbor        0.3 bin
+neigh_modify    every 20 one 50
+comm_modify     cutoff * 20
+fix             1 all nve
+thermo          10
+run             {steps}
+"""
+
+
+def cbnmd_leg(cells, steps):
+    """Run the C++ driver on an in.lj deck and report what ITS summary prints (wall clock of the
+    step loop, reference format `#Steps/s Atomsteps/s Atomsteps/(proc*s)`, cabanamd_impl.h:418-428)."""
+    import subprocess
+    import tempfile
+
+    exe = os.path.join(ROOT, "cabanamd_b200", "lib", "cbnMD")
+    if not os.path.exists(exe):
+        return None
+    with tempfile.TemporaryDirectory() as td:
+        deck = os.path.join(td, "in.lj")
+        with open(deck, "w") as f:
+            f.write(IN_LJ.format(c=cells, steps=steps))
+        out = os.path.join(td, "md.out")
+        try:
+            p = subprocess.run([exe, "-il", deck, "-o", out, "-e", os.path.join(td, "md.err")],
+                               capture_output=True, text=True, cwd=td, timeout=600)
+        except subprocess.TimeoutExpired:
+            return {"error": "timeout"}
+        txt = open(out).read() if os.path.exists(out) else ""
+        if p.returncode != 0 or "#Steps/s" not in txt:
+            return {"error": (p.stderr or txt)[-300:]}
+        lines = txt.splitlines()
+        k = max(i for i, ln in enumerate(lines) if ln.startswith("#Steps/s"))
+        sps, aps, _ = (float(v) for v in lines[k + 1].split())
+        thermo = [ln.split() for ln in lines[:k] if ln and ln[0].isdigit() and len(ln.split()) == 6]
+        res = {"value": aps, "unit": UNIT, "steps_per_s": sps, "atoms": 4 * cells ** 3,
+               "timing": "host wall clock around the step loop, as the reference prints it"}
+        if thermo:
+            res["etot_first_last"] = [float(thermo[0][3]), float(thermo[-1][3])]
+        return res
+
+
 def timed_steps(sim, md_steps, thermo, dist_ctx):
     """md_steps MD steps bracketed by barrier + synchronize, CUDA events on the context
     stream; returns seconds (max over ranks)."""
@@ -672,6 +726,13 @@ def main():
             "force_kernel_frac_of_peak": fb5 / (f_ms / max(f_n, 1) * 1e-3) / 1e9 / peak,
             "stored_neighbours_per_atom": m5["nn"], "ghost_fraction": m5["n_ghost"] / m5["n_local"]}
         s5.ctx.close()
+    if n == 1 and not args.no_extra:
+        # the product driver itself: the C++ step loop (cabanamd_b200/host, binary cbnMD) on configs[0]
+        # (input/in.lj as shipped: 20^3 fcc cells) and on the headline workload — no Python in the loop
+        for cells, steps in ((20, 2000), (args.cells, 200)):
+            r = cbnmd_leg(cells, steps)
+            if r:
+                extra[f"cbnMD (C++ driver) in.lj, {4 * cells ** 3} atoms, {steps} steps"] = r
     if not args.no_extra:
         # configs[3]: 16.4 M atoms strong scaling on the N GPUs + the drift check vs the oracle
         ss = strong_scaling_leg(args, n, rank, local, dist_ctx)

@@ -6,6 +6,6 @@ lib/libcbmd_cuda.so (kernels + C ABI) and the C++ host classes under host/.
 There is no CPU fallback: loading fails loudly when the library is missing and
 context creation fails when no sm_100 device is present.
 """
-from .capi import Context, CbmdError, load_library, library_path, declared_symbols  # noqa: F401
+from .capi import Context, Hub, CbmdError, load_library, library_path, declared_symbols  # noqa: F401
 
 __version__ = "0.1"

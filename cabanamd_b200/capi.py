@@ -85,6 +85,9 @@ def load_library():
     L.cbmd_comm_unique_id.argtypes = [vp]
     L.cbmd_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.cbmd_comm_rank.argtypes = [vp, c_ip, c_ip]
+    L.cbmd_hub_create.argtypes = [C.POINTER(vp), C.c_int, C.c_double]
+    L.cbmd_hub_destroy.argtypes = [vp]
+    L.cbmd_comm_init_hub.argtypes = [vp, vp, C.c_int]
     L.cbmd_exchange.argtypes = [vp, c_ip]
     L.cbmd_exchange_halo.argtypes = [vp, C.c_double]
     L.cbmd_update_halo.argtypes = [vp]
@@ -140,6 +143,25 @@ def make_domain(glo, ghi, nranks, rank, ghost_cutoff):
     return dict(glo=glo, ghi=ghi, grid=grid, pos=pos,
                 llo=glo + cell * off, lhi=glo + cell * (off + 100),
                 ghost_lo=glo + cell * (off - halo), ghost_hi=glo + cell * (off + 100 + halo))
+
+
+class Hub:
+    """In-process transport between `nranks` contexts, each driven by its own host thread
+    (cbmd_hub_create).  Lets one GPU run the decomposed path at 2/4/8 ranks."""
+
+    def __init__(self, nranks, timeout=120.0):
+        self.L = load_library()
+        self.nranks = int(nranks)
+        h = C.c_void_p()
+        if self.L.cbmd_hub_create(C.byref(h), self.nranks, float(timeout)) != 0:
+            raise CbmdError(self.L.cbmd_last_error().decode())
+        self.h = h
+
+    def close(self):
+        if self.h:
+            if self.L.cbmd_hub_destroy(self.h) != 0:
+                raise CbmdError(self.L.cbmd_last_error().decode())
+            self.h = None
 
 
 class Context:
@@ -306,6 +328,13 @@ class Context:
         return buf.raw
 
     def comm_init(self, nranks=1, rank=0, uid=None):
+        """uid: the 128-byte NCCL id (one process per GPU), or a Hub (ranks = host threads of
+        this process, in-process transport)."""
+        if isinstance(uid, Hub):
+            assert nranks == uid.nranks, (nranks, uid.nranks)
+            self._ck(self.L.cbmd_comm_init_hub(self.h, uid.h, rank))
+            self._hub = uid  # keep the hub alive as long as this context is attached
+            return
         buf = None if uid is None else C.create_string_buffer(uid, 128)
         self._ck(self.L.cbmd_comm_init(self.h, nranks, rank, buf))
 

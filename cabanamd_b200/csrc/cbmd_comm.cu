@@ -26,6 +26,148 @@ static int rank_of_pos( const int grid[3], int i, int j, int k )
 }
 
 // ---------------------------------------------------------------------------
+// Transport: one group of point-to-point messages, all in flight together.  Between processes
+// it is an NCCL group (ncclSend/ncclRecv on the given stream); between contexts of one process
+// (cbmd_comm_init_hub) the messages go through the hub's FIFOs as device-to-device copies
+// ordered by events.  Both pair messages of one (source, destination) in posting order.
+// ---------------------------------------------------------------------------
+static void hub_fail( cbmd_hub *hub, const char *what )
+{
+    hub->failed = true;
+    hub->cv.notify_all();
+    throw CbmdError( std::string( "hub: " ) + what + " (a peer did not reach the matching call within " +
+                     std::to_string( (int)hub->timeout_s ) + " s, or failed earlier)" );
+}
+
+template <class Pred>
+static void hub_wait( cbmd_hub *hub, std::unique_lock<std::mutex> &lk, Pred pred, const char *what )
+{
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::duration<double>( hub->timeout_s );
+    while ( !pred() )
+    {
+        if ( hub->failed )
+            hub_fail( hub, what );
+        if ( hub->cv.wait_until( lk, deadline ) == std::cv_status::timeout && !pred() )
+            hub_fail( hub, what );
+    }
+}
+
+// rank-synchronous barrier over the hub (generation counted)
+static void hub_barrier( cbmd_hub *hub, std::unique_lock<std::mutex> &lk )
+{
+    const long gen = hub->generation;
+    if ( ++hub->arrived == hub->nranks )
+    {
+        hub->arrived = 0;
+        hub->generation++;
+        hub->cv.notify_all();
+        return;
+    }
+    hub_wait( hub, lk, [&] { return hub->generation != gen; }, "barrier" );
+}
+
+// release the `done` events whose senders have ordered themselves behind them
+static void hub_collect( cbmd_ctx *ctx, bool all )
+{
+    auto &v = ctx->hub_done;
+    size_t keep = 0;
+    for ( size_t k = 0; k < v.size(); k++ )
+    {
+        if ( all || v[k]->state == 2 )
+            cudaEventDestroy( v[k]->done );
+        else
+            v[keep++] = v[k];
+    }
+    v.resize( keep );
+}
+
+struct Xfer
+{
+    struct Op
+    {
+        void *ptr;
+        size_t bytes;
+        int peer;
+    };
+    cbmd_ctx *ctx;
+    cudaStream_t s;
+    std::vector<Op> sends, recvs;
+    Xfer( cbmd_ctx *c, cudaStream_t st ) : ctx( c ), s( st ) {}
+    void send( const void *p, size_t bytes, int peer )
+    {
+        if ( bytes > 0 )
+            sends.push_back( { const_cast<void *>( p ), bytes, peer } );
+    }
+    void recv( void *p, size_t bytes, int peer )
+    {
+        if ( bytes > 0 )
+            recvs.push_back( { p, bytes, peer } );
+    }
+    void run()
+    {
+        if ( sends.empty() && recvs.empty() )
+            return;
+        if ( !ctx->hub )
+        {
+            CBMD_REQUIRE( ctx->nccl != nullptr, "no communicator: call cbmd_comm_init first" );
+            CBMD_NCCL( ncclGroupStart() );
+            for ( const Op &o : sends )
+                CBMD_NCCL( ncclSend( o.ptr, o.bytes, ncclChar, o.peer, ctx->nccl, s ) );
+            for ( const Op &o : recvs )
+                CBMD_NCCL( ncclRecv( o.ptr, o.bytes, ncclChar, o.peer, ctx->nccl, s ) );
+            CBMD_NCCL( ncclGroupEnd() );
+            return;
+        }
+        cbmd_hub *hub = ctx->hub;
+        const int np = hub->nranks, me = ctx->rank;
+        cudaEvent_t ready = nullptr;
+        std::vector<std::shared_ptr<HubMsg>> posted;
+        if ( !sends.empty() )
+        {
+            CBMD_CUDA( cudaEventCreateWithFlags( &ready, cudaEventDisableTiming ) );
+            CBMD_CUDA( cudaEventRecord( ready, s ) );
+        }
+        std::unique_lock<std::mutex> lk( hub->m );
+        hub_collect( ctx, false );
+        for ( const Op &o : sends )
+        {
+            auto m = std::make_shared<HubMsg>();
+            m->ptr = o.ptr;
+            m->bytes = o.bytes;
+            m->ready = ready;
+            hub->q[(size_t)me * np + o.peer].push_back( m );
+            posted.push_back( m );
+        }
+        hub->cv.notify_all();
+        for ( const Op &o : recvs )
+        {
+            auto &q = hub->q[(size_t)o.peer * np + me];
+            hub_wait( hub, lk, [&] { return !q.empty(); }, "receive" );
+            std::shared_ptr<HubMsg> m = q.front();
+            q.pop_front();
+            if ( m->bytes != o.bytes )
+                hub_fail( hub, "message size differs from what the receiver expects" );
+            CBMD_CUDA( cudaStreamWaitEvent( s, m->ready, 0 ) );
+            CBMD_CUDA( cudaMemcpyAsync( o.ptr, m->ptr, o.bytes, cudaMemcpyDefault, s ) );
+            CBMD_CUDA( cudaEventCreateWithFlags( &m->done, cudaEventDisableTiming ) );
+            CBMD_CUDA( cudaEventRecord( m->done, s ) );
+            m->state = 1;
+            ctx->hub_done.push_back( m );
+            hub->cv.notify_all();
+        }
+        for ( auto &m : posted )
+        {
+            hub_wait( hub, lk, [&] { return m->state >= 1; }, "send" );
+            CBMD_CUDA( cudaStreamWaitEvent( s, m->done, 0 ) );
+            m->state = 2;
+        }
+        lk.unlock();
+        if ( ready )
+            CBMD_CUDA( cudaEventDestroy( ready ) ); // every receiver has ordered its stream behind it
+    }
+};
+
+// ---------------------------------------------------------------------------
 // ordered stream compaction of indices i in [0,n) with coordinate test in dim d:
 //   mode 0: x_d >= thr   mode 1: x_d <= thr   mode 2: x_d > thr   mode 3: x_d < thr
 // ---------------------------------------------------------------------------
@@ -104,12 +246,12 @@ static void select_pair( cbmd_ctx *ctx, int n, int d, const int mode[2], const d
     {
         // with two ranks in this dimension both messages go to the same peer: sends and
         // receives are issued in phase order on both sides, which is how NCCL pairs them
-        CBMD_NCCL( ncclGroupStart() );
+        Xfer x( ctx, s );
         for ( int k = 0; k < 2; k++ )
-            CBMD_NCCL( ncclSend( d_cnt + k, 1, ncclInt, peer_send[k], ctx->nccl, s ) );
+            x.send( d_cnt + k, sizeof( int ), peer_send[k] );
         for ( int k = 0; k < 2; k++ )
-            CBMD_NCCL( ncclRecv( d_in + k, 1, ncclInt, peer_recv[k], ctx->nccl, s ) );
-        CBMD_NCCL( ncclGroupEnd() );
+            x.recv( d_in + k, sizeof( int ), peer_recv[k] );
+        x.run();
         CBMD_CUDA( cudaMemcpyAsync( ctx->h_pinned_i + 10, d_in, 2 * sizeof( int ), cudaMemcpyDeviceToHost, s ) );
     }
     CBMD_CUDA( cudaStreamSynchronize( s ) );
@@ -348,18 +490,14 @@ extern "C" int cbmd_exchange( cbmd_ctx *ctx, int *n_sent_global )
             std::swap( ctx->id, ctx->id_alt );
             std::swap( ctx->q, ctx->q_alt );
         }
-        CBMD_NCCL( ncclGroupStart() );
-        if ( n_send[0] > 0 )
-            CBMD_NCCL( ncclSend( sb, (size_t)n_send[0] * sizeof( MigTuple ), ncclChar, peer_send[0], ctx->nccl, s ) );
-        if ( n_send[1] > 0 )
-            CBMD_NCCL( ncclSend( sb + n_send[0], (size_t)n_send[1] * sizeof( MigTuple ), ncclChar, peer_send[1],
-                                 ctx->nccl, s ) );
-        if ( n_recv[0] > 0 )
-            CBMD_NCCL( ncclRecv( rb, (size_t)n_recv[0] * sizeof( MigTuple ), ncclChar, peer_recv[0], ctx->nccl, s ) );
-        if ( n_recv[1] > 0 )
-            CBMD_NCCL( ncclRecv( rb + n_recv[0], (size_t)n_recv[1] * sizeof( MigTuple ), ncclChar, peer_recv[1],
-                                 ctx->nccl, s ) );
-        CBMD_NCCL( ncclGroupEnd() );
+        {
+            Xfer x( ctx, s );
+            x.send( sb, (size_t)n_send[0] * sizeof( MigTuple ), peer_send[0] );
+            x.send( sb + n_send[0], (size_t)n_send[1] * sizeof( MigTuple ), peer_send[1] );
+            x.recv( rb, (size_t)n_recv[0] * sizeof( MigTuple ), peer_recv[0] );
+            x.recv( rb + n_recv[0], (size_t)n_recv[1] * sizeof( MigTuple ), peer_recv[1] );
+            x.run();
+        }
         const int n_keep = n - ns;
         ctx->n_local = n_keep; // so a regrow copies only live rows
         cbmd_ensure_capacity( ctx, n_keep + nr );
@@ -637,7 +775,21 @@ static void build_flat_plan( cbmd_ctx *ctx )
         cbmd_exclusive_scan_int( ctx, pos, ng );
         CBMD_CUDA( cudaMemcpyAsync( d_cnt + p, pos + ng, sizeof( int ), cudaMemcpyDeviceToDevice, s ) );
     }
-    CBMD_NCCL( ncclAllGather( d_cnt, d_all, np, ncclInt, ctx->nccl, s ) );
+    if ( ctx->hub )
+    {
+        Xfer x( ctx, s );
+        for ( int p = 0; p < np; p++ )
+            if ( p != me )
+            {
+                x.send( d_cnt, (size_t)np * sizeof( int ), p );
+                x.recv( d_all + (size_t)p * np, (size_t)np * sizeof( int ), p );
+            }
+        CBMD_CUDA( cudaMemcpyAsync( d_all + (size_t)me * np, d_cnt, (size_t)np * sizeof( int ),
+                                    cudaMemcpyDeviceToDevice, s ) );
+        x.run();
+    }
+    else
+        CBMD_NCCL( ncclAllGather( d_cnt, d_all, np, ncclInt, ctx->nccl, s ) );
     std::vector<int> all( (size_t)np * np );
     CBMD_CUDA( cudaMemcpyAsync( all.data(), d_all, all.size() * sizeof( int ), cudaMemcpyDeviceToHost, s ) );
     CBMD_CUDA( cudaStreamSynchronize( s ) );
@@ -672,17 +824,17 @@ static void build_flat_plan( cbmd_ctx *ctx )
         CBMD_LAUNCH_CHECK( ctx );
     }
     // request lists to the roots; what the others want from me comes back
-    CBMD_NCCL( ncclGroupStart() );
-    for ( int p = 0; p < np; p++ )
     {
-        if ( p == me )
-            continue;
-        if ( ctx->rcnt[p] > 0 )
-            CBMD_NCCL( ncclSend( req + ctx->roff[p], ctx->rcnt[p], ncclInt, p, ctx->nccl, s ) );
-        if ( ctx->scnt[p] > 0 )
-            CBMD_NCCL( ncclRecv( ctx->export_idx + ctx->soff[p], ctx->scnt[p], ncclInt, p, ctx->nccl, s ) );
+        Xfer x( ctx, s );
+        for ( int p = 0; p < np; p++ )
+        {
+            if ( p == me )
+                continue;
+            x.send( req + ctx->roff[p], (size_t)ctx->rcnt[p] * sizeof( int ), p );
+            x.recv( ctx->export_idx + ctx->soff[p], (size_t)ctx->scnt[p] * sizeof( int ), p );
+        }
+        x.run();
     }
-    CBMD_NCCL( ncclGroupEnd() );
     ensure_buf( ctx->sendbuf, ctx->sendbuf_bytes, 3 * (size_t)( so + 1 ) * sizeof( double ), s );
     ensure_buf( ctx->recvbuf, ctx->recvbuf_bytes, 3 * (size_t)( ro + 1 ) * sizeof( double ), s );
     // (req lives in scratch: later users of scratch are ordered behind the sends on this stream)
@@ -776,16 +928,14 @@ extern "C" int cbmd_exchange_halo( cbmd_ctx *ctx, double comm_depth )
                         n_send[k], ctx->n_local, ctx->rank, sx[k] );
                     CBMD_LAUNCH_CHECK( ctx );
                 }
-            CBMD_NCCL( ncclGroupStart() );
-            for ( int k = 0; k < 2; k++ )
-                if ( n_send[k] > 0 )
-                    CBMD_NCCL( ncclSend( sx[k], (size_t)n_send[k] * sizeof( HaloRec ), ncclChar, peer_send[k],
-                                         ctx->nccl, s ) );
-            for ( int k = 0; k < 2; k++ )
-                if ( n_recv[k] > 0 )
-                    CBMD_NCCL( ncclRecv( rx[k], (size_t)n_recv[k] * sizeof( HaloRec ), ncclChar, peer_recv[k],
-                                         ctx->nccl, s ) );
-            CBMD_NCCL( ncclGroupEnd() );
+            {
+                Xfer x( ctx, s );
+                for ( int k = 0; k < 2; k++ )
+                    x.send( sx[k], (size_t)n_send[k] * sizeof( HaloRec ), peer_send[k] );
+                for ( int k = 0; k < 2; k++ )
+                    x.recv( rx[k], (size_t)n_recv[k] * sizeof( HaloRec ), peer_recv[k] );
+                x.run();
+            }
             for ( int k = 0; k < 2; k++ )
                 if ( n_recv[k] > 0 )
                 {
@@ -896,19 +1046,17 @@ extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
                                                                          ctx->sendbuf );
             CBMD_LAUNCH_CHECK( ctx );
         }
-        CBMD_NCCL( ncclGroupStart() );
-        for ( int p = 0; p < ctx->nranks; p++ )
         {
-            if ( p == ctx->rank )
-                continue;
-            if ( ctx->scnt[p] > 0 )
-                CBMD_NCCL( ncclSend( ctx->sendbuf + 3 * (size_t)ctx->soff[p], 3 * (size_t)ctx->scnt[p], ncclDouble, p,
-                                     ctx->nccl, s ) );
-            if ( ctx->rcnt[p] > 0 )
-                CBMD_NCCL( ncclRecv( ctx->recvbuf + 3 * (size_t)ctx->roff[p], 3 * (size_t)ctx->rcnt[p], ncclDouble, p,
-                                     ctx->nccl, s ) );
+            Xfer x( ctx, s );
+            for ( int p = 0; p < ctx->nranks; p++ )
+            {
+                if ( p == ctx->rank )
+                    continue;
+                x.send( ctx->sendbuf + 3 * (size_t)ctx->soff[p], 3 * (size_t)ctx->scnt[p] * sizeof( double ), p );
+                x.recv( ctx->recvbuf + 3 * (size_t)ctx->roff[p], 3 * (size_t)ctx->rcnt[p] * sizeof( double ), p );
+            }
+            x.run();
         }
-        CBMD_NCCL( ncclGroupEnd() );
         const bool live = cbmd_mirror_live( ctx );
         k_halo_unpack_flat<<<div_up( ctx->n_ghost, 256 ), 256, 0, s>>>(
             ctx->xt, ctx->n_local, ctx->n_ghost, ctx->ghost_owner, ctx->ghost_rank, ctx->ghost_image, ctx->ghost_slot,
@@ -953,16 +1101,14 @@ extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
             }
         // with two ranks in this dimension both phases talk to the same peer: sends and
         // receives are issued in phase order on both sides, which is how NCCL pairs them
-        CBMD_NCCL( ncclGroupStart() );
-        for ( int k = 0; k < 2; k++ )
-            if ( pair[k]->n_send > 0 )
-                CBMD_NCCL( ncclSend( sx[k], (size_t)pair[k]->n_send * sizeof( XT ), ncclChar,
-                                     pair[k]->peer_send, ctx->nccl, s ) );
-        for ( int k = 0; k < 2; k++ )
-            if ( pair[k]->n_recv > 0 )
-                CBMD_NCCL( ncclRecv( ctx->xt + pair[k]->recv_first, (size_t)pair[k]->n_recv * sizeof( XT ),
-                                     ncclChar, pair[k]->peer_recv, ctx->nccl, s ) );
-        CBMD_NCCL( ncclGroupEnd() );
+        {
+            Xfer x( ctx, s );
+            for ( int k = 0; k < 2; k++ )
+                x.send( sx[k], (size_t)pair[k]->n_send * sizeof( XT ), pair[k]->peer_send );
+            for ( int k = 0; k < 2; k++ )
+                x.recv( ctx->xt + pair[k]->recv_first, (size_t)pair[k]->n_recv * sizeof( XT ), pair[k]->peer_recv );
+            x.run();
+        }
         for ( HaloPhase *P : pair )
             if ( P->n_recv > 0 && P->shift != 0.0 )
             {
@@ -1018,17 +1164,15 @@ extern "C" int cbmd_update_force( cbmd_ctx *ctx )
         }
         // ghosts I received in this phase go back to peer_recv; what I sent comes back from peer_send
         ensure_buf( ctx->recvbuf, ctx->recvbuf_bytes, 3 * (size_t)( P.n_send + 1 ) * sizeof( double ), s );
-        CBMD_NCCL( ncclGroupStart() );
-        for ( int c = 0; c < 3; c++ )
         {
-            if ( P.n_recv > 0 )
-                CBMD_NCCL( ncclSend( ctx->f + (size_t)c * ctx->cap + P.recv_first, P.n_recv,
-                                     ncclDouble, P.peer_recv, ctx->nccl, s ) );
-            if ( P.n_send > 0 )
-                CBMD_NCCL( ncclRecv( ctx->recvbuf + (size_t)c * P.n_send, P.n_send, ncclDouble,
-                                     P.peer_send, ctx->nccl, s ) );
+            Xfer x( ctx, s );
+            for ( int c = 0; c < 3; c++ )
+            {
+                x.send( ctx->f + (size_t)c * ctx->cap + P.recv_first, (size_t)P.n_recv * sizeof( double ), P.peer_recv );
+                x.recv( ctx->recvbuf + (size_t)c * P.n_send, (size_t)P.n_send * sizeof( double ), P.peer_send );
+            }
+            x.run();
         }
-        CBMD_NCCL( ncclGroupEnd() );
         if ( P.n_send > 0 )
         {
             k_force_fold<<<div_up( P.n_send, 256 ), 256, 0, s>>>( ctx->f, ctx->cap, P.send_idx,
@@ -1069,6 +1213,7 @@ extern "C" int cbmd_comm_init( cbmd_ctx *ctx, int nranks, int rank, const void *
         CBMD_NCCL( ncclCommDestroy( ctx->nccl ) );
         ctx->nccl = nullptr;
     }
+    cbmd_hub_detach( ctx );
     ctx->nranks = nranks;
     ctx->rank = rank;
     if ( nranks > 1 )
@@ -1079,6 +1224,100 @@ extern "C" int cbmd_comm_init( cbmd_ctx *ctx, int nranks, int rank, const void *
         CBMD_NCCL( ncclCommInitRank( &ctx->nccl, nranks, id, rank ) );
     }
     CBMD_API_END
+}
+
+// ---- in-process transport (include/cbmd_c_api.h: cbmd_hub_create) ----------------------------
+extern "C" int cbmd_hub_create( cbmd_hub **out, int nranks, double timeout_seconds )
+{
+    try
+    {
+        if ( !out || nranks < 1 || nranks > 64 )
+            throw CbmdError( "cbmd_hub_create: bad arguments (1 <= nranks <= 64)" );
+        cbmd_hub *h = new cbmd_hub();
+        h->nranks = nranks;
+        h->timeout_s = timeout_seconds > 0 ? timeout_seconds : 120.0;
+        h->q.resize( (size_t)nranks * nranks );
+        h->slot.assign( nranks, std::vector<char>( 1024 ) );
+        *out = h;
+        return 0;
+    }
+    catch ( const std::exception &e )
+    {
+        cbmd_set_error( e.what() );
+        return 1;
+    }
+}
+
+extern "C" int cbmd_hub_destroy( cbmd_hub *hub )
+{
+    if ( !hub )
+        return 0;
+    {
+        std::unique_lock<std::mutex> lk( hub->m );
+        if ( hub->attached > 0 )
+        {
+            cbmd_set_error( "cbmd_hub_destroy: contexts are still attached (destroy or re-init them first)" );
+            return 1;
+        }
+    }
+    delete hub;
+    return 0;
+}
+
+void cbmd_hub_detach( cbmd_ctx *ctx )
+{
+    if ( !ctx->hub )
+        return;
+    // nobody may still wait on one of my events: drain my streams, then drop them
+    cudaStreamSynchronize( ctx->stream );
+    if ( ctx->comm_stream )
+        cudaStreamSynchronize( ctx->comm_stream );
+    std::unique_lock<std::mutex> lk( ctx->hub->m );
+    hub_collect( ctx, true );
+    ctx->hub->attached--;
+    ctx->hub = nullptr;
+}
+
+extern "C" int cbmd_comm_init_hub( cbmd_ctx *ctx, cbmd_hub *hub, int rank )
+{
+    CBMD_API_BEGIN
+    CBMD_REQUIRE( hub != nullptr, "null hub" );
+    CBMD_REQUIRE( rank >= 0 && rank < hub->nranks, "bad rank for this hub" );
+    if ( ctx->nccl )
+    {
+        CBMD_NCCL( ncclCommDestroy( ctx->nccl ) );
+        ctx->nccl = nullptr;
+    }
+    cbmd_hub_detach( ctx );
+    ctx->nranks = hub->nranks;
+    ctx->rank = rank;
+    if ( hub->nranks > 1 )
+    {
+        std::unique_lock<std::mutex> lk( hub->m );
+        ctx->hub = hub;
+        hub->attached++;
+    }
+    CBMD_API_END
+}
+
+// scalar collectives between the contexts of a hub: every rank deposits its values, all
+// combine them in rank order (the same order on every rank: identical results everywhere)
+template <class T, class Op>
+static void hub_combine( cbmd_ctx *ctx, T *vals, int count, Op op, bool prefix )
+{
+    cbmd_hub *hub = ctx->hub;
+    std::unique_lock<std::mutex> lk( hub->m );
+    memcpy( hub->slot[ctx->rank].data(), vals, count * sizeof( T ) );
+    hub_barrier( hub, lk );
+    const int last = prefix ? ctx->rank : hub->nranks - 1;
+    for ( int k = 0; k < count; k++ )
+    {
+        T acc = ( (const T *)hub->slot[0].data() )[k];
+        for ( int r = 1; r <= last; r++ )
+            acc = op( acc, ( (const T *)hub->slot[r].data() )[k] );
+        vals[k] = acc;
+    }
+    hub_barrier( hub, lk ); // slots are free again
 }
 
 extern "C" int cbmd_comm_rank( cbmd_ctx *ctx, int *rank, int *nranks )
@@ -1097,6 +1336,14 @@ static void allreduce_small( cbmd_ctx *ctx, T *vals, int count, ncclDataType_t d
     if ( ctx->nranks == 1 || count == 0 )
         return;
     CBMD_REQUIRE( count * sizeof( T ) <= 1024, "scalar reductions are limited to 1 KiB" );
+    if ( ctx->hub )
+    {
+        if ( op == ncclSum )
+            hub_combine( ctx, vals, count, []( T a, T b ) { return a + b; }, false );
+        else
+            hub_combine( ctx, vals, count, []( T a, T b ) { return a > b ? a : b; }, false );
+        return;
+    }
     cudaStream_t s = ctx->stream;
     void *d = (void *)( ctx->d_red + 40000 );
     CBMD_CUDA( cudaMemcpyAsync( d, vals, count * sizeof( T ), cudaMemcpyHostToDevice, s ) );
@@ -1136,6 +1383,12 @@ extern "C" int cbmd_scan_sum_int( cbmd_ctx *ctx, int *vals, int count )
     if ( ctx->nranks > 1 && count > 0 )
     {
         CBMD_REQUIRE( (size_t)count * ctx->nranks * sizeof( int ) <= 4096, "scan too large" );
+        if ( ctx->hub )
+        {
+            CBMD_REQUIRE( count * sizeof( int ) <= 1024, "scan too large" );
+            hub_combine( ctx, vals, count, []( int a, int b ) { return a + b; }, true );
+            return 0;
+        }
         cudaStream_t s = ctx->stream;
         int *d = (int *)( ctx->d_red + 41000 );
         CBMD_CUDA( cudaMemcpyAsync( d + (size_t)ctx->rank * count, vals, count * sizeof( int ),

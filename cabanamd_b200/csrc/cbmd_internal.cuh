@@ -5,9 +5,14 @@
 #include <nccl.h>
 #include <nvtx3/nvToolsExt.h> // header-only NVTX 3: ranges around the module entry points (option "nvtx")
 
+#include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -81,6 +86,36 @@ struct HaloPhase
     int peer_send = -1, peer_recv = -1;
 };
 
+// ---------------------------------------------------------------------------
+// In-process transport (cbmd_hub_create): one FIFO of posted messages per (source, destination)
+// pair.  A message is {device pointer, bytes, event recorded by the sender}; the receiver
+// orders its stream behind that event, copies device to device and hands back an event of
+// its own that the sender's stream waits for before the send buffer is reused.
+// ---------------------------------------------------------------------------
+struct HubMsg
+{
+    const void *ptr = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t ready = nullptr; // sender's, recorded when the payload is complete
+    cudaEvent_t done = nullptr;  // receiver's, recorded behind its copy
+    int state = 0;               // 0 posted, 1 copied (done valid), 2 sender has ordered itself behind done
+};
+
+struct cbmd_hub
+{
+    int nranks = 1;
+    double timeout_s = 120.0;
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<std::deque<std::shared_ptr<HubMsg>>> q; // [src * nranks + dst]
+    // scalar collectives: one 1 KiB slot per rank + a generation barrier
+    std::vector<std::vector<char>> slot;
+    int arrived = 0;
+    long generation = 0;
+    int attached = 0;
+    bool failed = false; // a rank timed out: every later wait fails at once
+};
+
 struct cbmd_ctx
 {
     int device = 0;
@@ -111,6 +146,7 @@ struct cbmd_ctx
     MirrorPtrs mir = { nullptr, nullptr, nullptr, nullptr };
     void *mirror_buf = nullptr;
     int mirror_kind = 0, mirror_cap = 0;
+    int mirror_off = 0; // slide of the mirror, (-n_local) mod 16 entries (cbmd_force.cu ensure_mirror)
     cudaTextureObject_t tex_z = 0; // zs (8-byte texels) or zt (16-byte texels), by kind
     // value of `epoch` at which the owned / ghost part of the mirror was last consistent with
     // xt; the integrator and the one-rank halo refresh write the mirror themselves, anything
@@ -171,6 +207,8 @@ struct cbmd_ctx
     // comm
     int nranks = 1, rank = 0;
     ncclComm_t nccl = nullptr;
+    cbmd_hub *hub = nullptr;                       // in-process transport instead of NCCL (cbmd_comm_init_hub)
+    std::vector<std::shared_ptr<HubMsg>> hub_done; // my `done` events the senders may still be waiting on
     HaloPhase phase[6];
     double comm_depth = 0.0;
     bool have_halo = false;
@@ -367,6 +405,7 @@ inline int64_t div_up64( int64_t a, int64_t b ) { return ( a + b - 1 ) / b; }
 
 // internal host helpers implemented across the .cu files
 void cbmd_ensure_capacity( cbmd_ctx *ctx, int n );
+void cbmd_hub_detach( cbmd_ctx *ctx ); // cbmd_comm.cu
 inline void cbmd_join_halo( cbmd_ctx *ctx )
 {
     if ( ctx->halo_pending )

@@ -279,6 +279,7 @@ extern "C" int cbmd_destroy( cbmd_ctx *ctx )
         return 0;
     cudaSetDevice( ctx->device );
     cudaStreamSynchronize( ctx->stream );
+    cbmd_hub_detach( ctx );
     if ( ctx->comm_stream )
     {
         cudaStreamSynchronize( ctx->comm_stream );

@@ -25,6 +25,7 @@ extern "C"
 #endif
 
     typedef struct cbmd_ctx cbmd_ctx;
+    typedef struct cbmd_hub cbmd_hub; /* in-process transport between several contexts, see cbmd_hub_create */
 
     enum
     {
@@ -132,6 +133,18 @@ extern "C"
      * nranks (one process per GPU); nranks == 1 needs no id (may be NULL). */
     int cbmd_comm_init( cbmd_ctx *ctx, int nranks, int rank, const void *id128 );
     int cbmd_comm_rank( cbmd_ctx *ctx, int *rank, int *nranks );
+    /* Several ranks inside ONE process (sub-domains sharing a GPU, or one host thread per GPU):
+     * the hub carries what NCCL carries between processes — the same packed messages, as
+     * stream-ordered device copies between the contexts — so the whole decomposed path
+     * (migration, 6-phase ghost build, halo refresh, reverse force fold, scalar reductions)
+     * runs with nranks > 1 on a single device.  NCCL refuses two ranks on one GPU; this is
+     * how a 1-GPU box exercises Comm (comm_mpi_impl.h:191-441) at 2/4/8 ranks.  Every rank
+     * drives its context from its own host thread: the calls that communicate block until
+     * the peers reach the same call, like MPI.  A peer that does not arrive within
+     * timeout_seconds (<= 0: 120 s) fails the call instead of hanging. */
+    int cbmd_hub_create( cbmd_hub **out, int nranks, double timeout_seconds );
+    int cbmd_hub_destroy( cbmd_hub *hub );
+    int cbmd_comm_init_hub( cbmd_ctx *ctx, cbmd_hub *hub, int rank );
     /* Comm::exchange (:191-278): drop ghosts, PBC-wrap / migrate owned atoms;
      * returns the global number of migrated atoms */
     int cbmd_exchange( cbmd_ctx *ctx, int *n_sent_global );

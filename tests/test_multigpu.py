@@ -1,4 +1,7 @@
-"""N>1 coverage.  GPU: torchrun tests/mp_parity.py on 2 (and 4/8 when present) GPUs.
+"""N>1 coverage.  GPU: torchrun tests/mp_parity.py on 2 (and 4/8 when present) GPUs over NCCL; on ANY
+GPU box (one device is enough) the same comparison with the ranks as host threads of one process over
+the in-process hub (cbmd_hub_create) — migration, 6-phase ghost build, one-stage and staged halo refresh,
+reverse force fold and the scalar collectives at 2/4/8 ranks against the oracle's virtual ranks.
 CPU: world_size-2 gloo test of the host-side decomposition logic (lattice split, id scan,
 momentum reduction) against the oracle's virtual ranks."""
 import os
@@ -31,6 +34,62 @@ def test_multigpu_matches_oracle(n, half):
            os.path.join(ROOT, "tests", "mp_parity.py")] + (["--half"] if half else [])
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert p.returncode == 0 and "MP_PARITY_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+def _hub_parity(n, **kw):
+    sys.path[:0] = [p for p in (ROOT, os.path.join(ROOT, "tests")) if p not in sys.path]
+    from mp_parity import run_parity_threads
+
+    ok, worst = run_parity_threads(n, 0, **kw)
+    assert ok, worst
+    return worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_ranks_on_one_gpu_match_oracle(n, half):
+    """2/4/8 ranks ({2,1,1}, {2,2,1}, {2,2,2}) sharing cuda:0: thermo, per-id x/v/f and per-rank ghost
+    sets against the oracle with the same number of virtual ranks, thermo also against one rank."""
+    worst = _hub_parity(n, half=half)
+    assert f"thermo_vs_{n}rank" in worst and f"f_vs_{n}rank" in worst and "ghost_x_rank0" in worst
+
+
+@pytest.mark.gpu
+def test_ranks_on_one_gpu_three_in_a_row_and_fp32():
+    """Three ranks in x (distinct +x and -x peers, unlike the 2-rank torus) and the FP32 sweep at 4."""
+    _hub_parity(3, half=False)
+    _hub_parity(3, half=True)
+    _hub_parity(4, half=False, precision=32)
+
+
+@pytest.mark.gpu
+def test_ranks_on_one_gpu_staged_halo_and_no_overlap():
+    """The 3-stage refresh (option halo_stages 3) and the non-overlapped step give the same answers."""
+    os.environ["CBMD_HALO_STAGES"] = "3"
+    try:
+        _hub_parity(4, half=False)
+        _hub_parity(8, half=True)
+    finally:
+        del os.environ["CBMD_HALO_STAGES"]
+    os.environ["CBMD_OVERLAP"] = "0"
+    try:
+        _hub_parity(4, half=False)
+    finally:
+        del os.environ["CBMD_OVERLAP"]
+
+
+@pytest.mark.gpu
+def test_hub_peer_that_never_arrives_fails_instead_of_hanging():
+    import cabanamd_b200 as cb
+
+    hub = cb.Hub(2, timeout=1.0)
+    c = cb.Context(0)
+    c.comm_init(2, 0, hub)
+    with pytest.raises(cb.CbmdError, match="hub"):
+        c.reduce_sum_int(1)
+    c.close()
+    hub.close()
 
 
 # ---------------------------------------------------------------- CPU, gloo, world_size 2
