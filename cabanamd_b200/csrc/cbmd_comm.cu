@@ -1030,11 +1030,17 @@ extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
     }
     // multi-rank: the six dependent phases run on the comm stream so the force kernel can
     // start on the interior tiles meanwhile (cbmd_force_lj joins before the boundary tiles)
-    const bool ov = ctx->overlap && ctx->tiles_valid;
+    // early: cbmd_integrate_initial has moved the atoms this refresh reads in a launch of their own
+    // and recorded ev_x behind it — the refresh starts there, beside the bulk of the integrator
+    const bool early = ctx->early_posted && ctx->flat_mp_ok && ctx->overlap;
+    ctx->early_posted = false;
+    ctx->halo_early = false;
+    const bool ov = ctx->overlap && ( ctx->tiles_valid || early );
     cudaStream_t s = ov ? ctx->comm_stream : ctx->stream;
     if ( ov )
     {
-        CBMD_CUDA( cudaEventRecord( ctx->ev_x, ctx->stream ) );
+        if ( !early )
+            CBMD_CUDA( cudaEventRecord( ctx->ev_x, ctx->stream ) );
         CBMD_CUDA( cudaStreamWaitEvent( s, ctx->ev_x, 0 ) );
     }
     if ( ctx->flat_mp_ok )
@@ -1068,6 +1074,7 @@ extern "C" int cbmd_update_halo( cbmd_ctx *ctx )
         {
             CBMD_CUDA( cudaEventRecord( ctx->ev_halo, s ) );
             ctx->halo_pending = true;
+            ctx->halo_early = early; // the force sweep joins and runs as one launch
         }
         return 0;
     }

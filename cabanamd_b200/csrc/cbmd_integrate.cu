@@ -10,21 +10,41 @@
 // reference's host arithmetic (mul then add, two roundings).
 #include "cbmd_internal.cuh"
 
+// FUSED: final_integrate of step k followed by initial_integrate of step k+1 (same f):
+// v1 = v + dtfm*f; v2 = v1 + dtfm*f; x += dt*v2 — the identical sequence of roundings.
+// TILES: the launch covers n_tiles 32-atom tiles named by tile_list (a warp per tile) instead
+// of atoms 0..n — the boundary tiles first and the interior tiles after them, so that the ghost
+// refresh can start in between (cbmd_integrate_initial).
+template <bool FUSED, bool TILES>
 __global__ void __launch_bounds__( 256 )
-    k_integrate_initial( XT *__restrict__ xt, double *__restrict__ v, const double *__restrict__ f,
-                         int cap, int n, const __grid_constant__ MassTable mt, double dtv,
-                         const MirrorPtrs mir )
+    k_integrate_step( XT *__restrict__ xt, double *__restrict__ v, const double *__restrict__ f,
+                      int cap, int n, const __grid_constant__ MassTable mt, double dtv,
+                      const MirrorPtrs mir, const int *__restrict__ tile_list, int n_tiles )
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ( TILES )
+    {
+        const int t = i >> 5;
+        if ( t >= n_tiles )
+            return;
+        i = tile_list[t] * 32 + ( threadIdx.x & 31 );
+    }
     if ( i >= n )
         return;
     XT r = xt[i];
     const double dtfm = mt.dtfm[r.t];
     double vx = v[i], vy = v[(size_t)cap + i], vz = v[2 * (size_t)cap + i];
-    const double fx = f[i], fy = f[(size_t)cap + i], fz = f[2 * (size_t)cap + i];
-    vx = __dadd_rn( vx, __dmul_rn( dtfm, fx ) );
-    vy = __dadd_rn( vy, __dmul_rn( dtfm, fy ) );
-    vz = __dadd_rn( vz, __dmul_rn( dtfm, fz ) );
+    const double kx = __dmul_rn( dtfm, f[i] ), ky = __dmul_rn( dtfm, f[(size_t)cap + i] ),
+                 kz = __dmul_rn( dtfm, f[2 * (size_t)cap + i] );
+    vx = __dadd_rn( vx, kx );
+    vy = __dadd_rn( vy, ky );
+    vz = __dadd_rn( vz, kz );
+    if ( FUSED )
+    {
+        vx = __dadd_rn( vx, kx );
+        vy = __dadd_rn( vy, ky );
+        vz = __dadd_rn( vz, kz );
+    }
     r.x = __dadd_rn( r.x, __dmul_rn( dtv, vx ) );
     r.y = __dadd_rn( r.y, __dmul_rn( dtv, vy ) );
     r.z = __dadd_rn( r.z, __dmul_rn( dtv, vz ) );
@@ -48,35 +68,6 @@ __global__ void __launch_bounds__( 256 )
     v[(size_t)cap + i] = __dadd_rn( v[(size_t)cap + i], __dmul_rn( dtfm, f[(size_t)cap + i] ) );
     v[2 * (size_t)cap + i] =
         __dadd_rn( v[2 * (size_t)cap + i], __dmul_rn( dtfm, f[2 * (size_t)cap + i] ) );
-}
-
-// final_integrate of step k followed by initial_integrate of step k+1 (same f):
-// v1 = v + dtfm*f; v2 = v1 + dtfm*f; x += dt*v2 — the identical sequence of roundings
-__global__ void __launch_bounds__( 256 )
-    k_integrate_final_initial( XT *__restrict__ xt, double *__restrict__ v,
-                               const double *__restrict__ f, int cap, int n,
-                               const __grid_constant__ MassTable mt, double dtv,
-                               const MirrorPtrs mir )
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if ( i >= n )
-        return;
-    XT r = xt[i];
-    const double dtfm = mt.dtfm[r.t];
-    double vx = v[i], vy = v[(size_t)cap + i], vz = v[2 * (size_t)cap + i];
-    const double kx = __dmul_rn( dtfm, f[i] ), ky = __dmul_rn( dtfm, f[(size_t)cap + i] ),
-                 kz = __dmul_rn( dtfm, f[2 * (size_t)cap + i] );
-    vx = __dadd_rn( __dadd_rn( vx, kx ), kx );
-    vy = __dadd_rn( __dadd_rn( vy, ky ), ky );
-    vz = __dadd_rn( __dadd_rn( vz, kz ), kz );
-    r.x = __dadd_rn( r.x, __dmul_rn( dtv, vx ) );
-    r.y = __dadd_rn( r.y, __dmul_rn( dtv, vy ) );
-    r.z = __dadd_rn( r.z, __dmul_rn( dtv, vz ) );
-    v[i] = vx;
-    v[(size_t)cap + i] = vy;
-    v[2 * (size_t)cap + i] = vz;
-    xt[i] = r;
-    mirror_store( mir, i, r );
 }
 
 void cbmd_materialize_final( cbmd_ctx *ctx )
@@ -107,17 +98,51 @@ extern "C" int cbmd_integrate_initial( cbmd_ctx *ctx )
                       std::to_string( ctx->ntypes ) + " type(s)" );
     const bool fused = ctx->final_pending;
     ctx->final_pending = false;
+    ctx->early_posted = false;
     if ( n > 0 )
     {
         // every owned position is rewritten here: keep the force kernel's split mirror current
         const bool live = cbmd_mirror_live( ctx );
         const MirrorPtrs mir = cbmd_mirror_ptrs( ctx );
-        if ( fused )
-            k_integrate_final_initial<<<div_up( n, 256 ), 256, 0, ctx->stream>>>(
-                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt, mir );
+        // multi-rank one-stage refresh: every atom it reads (the roots of the ghosts: within the ghost
+        // depth of a face) lies in a BOUNDARY tile of the lists cbmd_neigh_build made, as long as that
+        // depth does not exceed the distance the tiles were classified with.  Those tiles go first; the
+        // refresh starts behind ev_x on the comm stream while the interior tiles are integrated here,
+        // and the force sweep that follows is ONE launch over all tiles (the alternative — the refresh
+        // beside the interior tiles of a split sweep — costs two launches and two tails, 0.026 ms per
+        // step at 4 M atoms)
+        const bool early = ctx->early_integrate && ctx->overlap && ctx->nranks > 1 && ctx->have_halo &&
+                           ctx->flat_mp_ok && ctx->tiles_valid && ctx->tiles_n_local == n &&
+                           ctx->comm_depth <= ctx->tiles_rcut && ctx->comm_stream != nullptr;
+#define CBMD_STEP( FUSED, TILES, LIST, COUNT )                                                      \
+    k_integrate_step<FUSED, TILES><<<div_up( TILES ? 32 * ( COUNT ) : ( COUNT ), 256 ), 256, 0, ctx->stream>>>( \
+        ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt, mir, LIST, COUNT )
+        if ( early )
+        {
+            const int *bl = ctx->tile_list + ctx->n_tiles_interior;
+            if ( ctx->n_tiles_boundary > 0 )
+            {
+                if ( fused )
+                    CBMD_STEP( true, true, bl, ctx->n_tiles_boundary );
+                else
+                    CBMD_STEP( false, true, bl, ctx->n_tiles_boundary );
+                CBMD_LAUNCH_CHECK( ctx );
+            }
+            CBMD_CUDA( cudaEventRecord( ctx->ev_x, ctx->stream ) );
+            ctx->early_posted = true;
+            if ( ctx->n_tiles_interior > 0 )
+            {
+                if ( fused )
+                    CBMD_STEP( true, true, ctx->tile_list, ctx->n_tiles_interior );
+                else
+                    CBMD_STEP( false, true, ctx->tile_list, ctx->n_tiles_interior );
+            }
+        }
+        else if ( fused )
+            CBMD_STEP( true, false, nullptr, n );
         else
-            k_integrate_initial<<<div_up( n, 256 ), 256, 0, ctx->stream>>>(
-                ctx->xt, ctx->v, ctx->f, ctx->cap, n, ctx->mass, ctx->dt, mir );
+            CBMD_STEP( false, false, nullptr, n );
+#undef CBMD_STEP
         CBMD_LAUNCH_CHECK( ctx );
         if ( live )
             ctx->mirror_owned_epoch = ctx->epoch;

@@ -221,6 +221,15 @@ struct cbmd_ctx
     // buffer, in ghost order (ghost_slot[g]); export side: export_idx[soff[p]..+scnt[p]) are the
     // owned atoms rank p wants every step, in the order rank p expects them.
     bool flat_mp_ok = false;
+    // option "early_integrate" 1: cbmd_integrate_initial moves the BOUNDARY tiles first (the tile lists
+    // of cbmd_neighbor.cu; every atom a ghost is an image of lies in one), so the one-stage refresh
+    // starts on the comm stream while the interior tiles are still being integrated and the force sweep
+    // is one launch.  Measured at N=2, 4 M atoms/GPU: force kernel 0.723 -> 0.698 ms, integrator 0.104 ->
+    // 0.116 ms, 8 us of the refresh exposed: +0.6 % (noise level), and the window it hides behind
+    // shrinks with the atoms per GPU — so the default stays 0: refresh beside the interior force tiles.
+    int early_integrate = 0;
+    bool early_posted = false; // integrate_initial recorded ev_x behind the early launch
+    bool halo_early = false;   // the pending refresh started from that event
     int *ghost_slot = nullptr; // [cap]
     int *export_idx = nullptr;
     int export_cap = 0, n_export = 0, n_import = 0;
@@ -239,6 +248,8 @@ struct cbmd_ctx
     int *tile_list = nullptr, *tile_flag = nullptr;
     int tile_cap = 0, n_tiles_interior = 0, n_tiles_boundary = 0;
     bool tiles_valid = false;
+    int tiles_n_local = -1;  // owned count the tile lists were made for
+    double tiles_rcut = 0.0; // distance from the faces that makes a tile a boundary tile
 
     // scratch
     void *scratch = nullptr;

@@ -780,6 +780,8 @@ static void build_tile_lists( cbmd_ctx *ctx, double rcut )
     CBMD_CUDA( cudaStreamSynchronize( s ) );
     ctx->n_tiles_boundary = ctx->h_pinned_i[2];
     ctx->n_tiles_interior = n_tiles - ctx->n_tiles_boundary;
+    ctx->tiles_n_local = ctx->n_local;
+    ctx->tiles_rcut = rcut;
     ctx->tiles_valid = true;
 }
 
@@ -1026,6 +1028,19 @@ extern "C" int64_t cbmd_table_size( int n_atoms, int row_capacity )
     return (int64_t)nb_table_size( ( n_atoms + 31 ) & ~31, ( row_capacity + 3 ) & ~3 );
 }
 
+// sum of the row lengths on the device (integer sum: order does not matter)
+__global__ void __launch_bounds__( 256 )
+    k_count_sum( const int *__restrict__ count, int n, unsigned long long *__restrict__ out )
+{
+    unsigned long long t = 0;
+    for ( int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x )
+        t += (unsigned long long)count[i];
+    for ( int o = 16; o > 0; o >>= 1 )
+        t += __shfl_down_sync( 0xffffffffu, t, o );
+    if ( ( threadIdx.x & 31 ) == 0 && t )
+        atomicAdd( out, t );
+}
+
 extern "C" int cbmd_neigh_sizes( cbmd_ctx *ctx, int64_t *total, int *max_neigh )
 {
     CBMD_API_BEGIN
@@ -1034,17 +1049,20 @@ extern "C" int cbmd_neigh_sizes( cbmd_ctx *ctx, int64_t *total, int *max_neigh )
         *max_neigh = ctx->nb_max;
     if ( total )
     {
-        std::vector<int> hc( n_local > 0 ? n_local : 1 );
-        int64_t t = 0;
+        *total = 0;
         if ( n_local > 0 )
         {
-            CBMD_CUDA( cudaMemcpyAsync( hc.data(), ctx->nb_pull ? ctx->nb_count_i : ctx->nb_count,
-                                        (size_t)n_local * sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ) );
-            CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );
-            for ( int i = 0; i < n_local; i++ )
-                t += hc[i];
+            cudaStream_t s = ctx->stream;
+            unsigned long long *d = (unsigned long long *)( ctx->d_flags + 28 ); // 8-byte aligned pair of ints
+            CBMD_CUDA( cudaMemsetAsync( d, 0, sizeof( unsigned long long ), s ) );
+            k_count_sum<<<std::min( div_up( n_local, 256 ), 1184 ), 256, 0, s>>>(
+                ctx->nb_pull ? ctx->nb_count_i : ctx->nb_count, n_local, d );
+            CBMD_LAUNCH_CHECK( ctx );
+            unsigned long long *h = (unsigned long long *)( ctx->h_pinned_i + 12 );
+            CBMD_CUDA( cudaMemcpyAsync( h, d, sizeof( unsigned long long ), cudaMemcpyDeviceToHost, s ) );
+            CBMD_CUDA( cudaStreamSynchronize( s ) );
+            *total = (int64_t)*h;
         }
-        *total = t;
     }
     CBMD_API_END
 }

@@ -230,6 +230,8 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
             ctx->overlap = atoi( e );
         if ( const char *e = getenv( "CBMD_HALO_STAGES" ) ) // A/B switch: 3 = per-dimension forwarding
             ctx->halo_stages = atoi( e ) == 3 ? 3 : 1;
+        if ( const char *e = getenv( "CBMD_EARLY" ) ) // A/B switch: 1 = refresh overlaps the integrator, one force launch
+            ctx->early_integrate = atoi( e ) != 0;
         if ( const char *e = getenv( "CBMD_GATHER" ) ) // A/B switch: 0 = 32-byte records by LDG.256
             ctx->gather_mode = atoi( e ) == 0 ? 0 : 1;
         if ( const char *e = getenv( "CBMD_HALF_KERNEL" ) ) // A/B switch: 0 = RED.ADD.F64 scatter
@@ -345,6 +347,13 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
         ctx->overlap = (int)value;
     else if ( n == "nvtx" )
         ctx->nvtx = value != 0.0;
+    else if ( n == "early_integrate" )
+    {
+        // multi-rank step with the one-stage refresh: 0 (default) = the exchange runs beside the interior
+        // tiles of a split force sweep; 1 = the boundary tiles are integrated first, the exchange runs
+        // beside the integration of the interior tiles and the force sweep is one launch
+        ctx->early_integrate = value != 0.0;
+    }
     else if ( n == "halo_stages" )
     {
         // multi-rank ghost refresh: 1 = every ghost straight from its root rank in one NCCL

@@ -218,9 +218,13 @@ extern "C"
      *   "halo_stages" 1 (default) multi-rank ghost refresh straight from the root ranks in one NCCL
      *               group; 3 = the reference's forwarding scheme, one group per dimension
      *   "nvtx"      1 = NVTX ranges (cbmd:Force, cbmd:Neigh, cbmd:Comm, ...) around the entry points
-     *   "overlap"   1 (default) halo refresh on a second stream under the interior force tiles
+     *   "overlap"   1 (default) multi-rank halo refresh on a second stream beside other work, 0 = in line
+     *   "early_integrate" 0 (default) the one-stage refresh runs beside the interior tiles of a split
+     *               force sweep; 1 = cbmd_integrate_initial moves the boundary tiles first, the refresh
+     *               runs beside the integration of the interior tiles and the force sweep is one launch
+     *               (+0.6 % at N=2 with 4 M atoms per GPU; the window shrinks with the atoms per GPU)
      * Environment overrides read at cbmd_create: CBMD_GATHER, CBMD_PRECISION, CBMD_NEIGH_KERNEL,
-     * CBMD_ROW_ORDER, CBMD_HALF_KERNEL, CBMD_HALO_STAGES, CBMD_OVERLAP. */
+     * CBMD_ROW_ORDER, CBMD_HALF_KERNEL, CBMD_HALO_STAGES, CBMD_OVERLAP, CBMD_EARLY. */
     int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value );
 
 #ifdef __cplusplus

@@ -77,6 +77,13 @@ def test_ranks_on_one_gpu_staged_halo_and_no_overlap():
         _hub_parity(4, half=False)
     finally:
         del os.environ["CBMD_OVERLAP"]
+    # one-stage refresh beside the integrator (boundary tiles first) instead of beside the interior force tiles
+    os.environ["CBMD_EARLY"] = "1"
+    try:
+        _hub_parity(4, half=False)
+        _hub_parity(2, half=True)
+    finally:
+        del os.environ["CBMD_EARLY"]
 
 
 @pytest.mark.gpu
