@@ -397,12 +397,14 @@ def measure_e2e(args, sim, steps, dist_ctx):
         {k: v * 1e3 for k, v in stage.items()}
 
 
-def oracle_threads():
-    """All host cores for the oracle (torchrun exports OMP_NUM_THREADS=1)."""
+def oracle_threads(busy_ranks=0):
+    """All host cores for the oracle (torchrun exports OMP_NUM_THREADS=1), less one per rank that
+    busy-waits in a collective meanwhile: OpenMP barriers spin, and spinning on oversubscribed
+    cores made the 8-virtual-rank drift check 15x slower than the 1-rank one (196 s against 13 s)."""
     import oracle_lib as O
 
     L = O.lib()
-    L.orc_set_threads(os.cpu_count() or 1)
+    L.orc_set_threads(max(1, (os.cpu_count() or 1) - busy_ranks))
     return L.orc_max_threads()
 
 
@@ -514,7 +516,7 @@ def drift_check(args, n, rank, local, dist_ctx, cells=40, md_steps=1000):
     if rank == 0:
         import oracle_lib as O
 
-        nthr = oracle_threads()
+        nthr = oracle_threads(busy_ranks=n - 1)  # the other ranks spin in the collective that follows
         t0 = time.perf_counter()
         ref = O.Sim(mass=[2.0]).create_lattice_fcc(cells=(cells,) * 3, nranks=n).setup()
         ref.record_thermo()

@@ -38,7 +38,7 @@ def simulate_rank(world, rank, device, uid, half=False, steps=45, cells=8, preci
     return sim, mine
 
 
-def compare_with_oracle(gathered, world, half=False, steps=45, cells=8, precision=64):
+def compare_with_oracle(gathered, world, half=False, steps=45, cells=8, precision=64, busy_ranks=0):
     """Every rank's state (list indexed by rank) against the CPU oracle run with `world` virtual
     ranks (thermo, per-id x/v/f, per-rank ghost sets) and with one rank (thermo).  Returns
     (ok, worst); `worst` maps check name -> largest deviation."""
@@ -47,7 +47,8 @@ def compare_with_oracle(gathered, world, half=False, steps=45, cells=8, precisio
 
     ok = True
     worst = {}
-    O.lib().orc_set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
+    # torchrun exports OMP_NUM_THREADS=1; ranks busy-waiting in a collective meanwhile keep a core each
+    O.lib().orc_set_threads(max(1, (os.cpu_count() or 1) - busy_ranks))
     grid = dims_create(world)
     cells3 = tuple(cells * k for k in grid)
     for nr in sorted({world, 1}, reverse=True):
@@ -122,7 +123,7 @@ def run_parity(world, rank, local, uid, half=False, steps=45, cells=8, precision
     dist.all_gather_object(gathered, mine)
     flag = [True, {}]
     if rank == 0:
-        flag = list(compare_with_oracle(gathered, world, half, steps, cells, precision))
+        flag = list(compare_with_oracle(gathered, world, half, steps, cells, precision, busy_ranks=world - 1))
     dist.broadcast_object_list(flag, src=0)
     sim.ctx.close()
     return flag[0], flag[1]
