@@ -732,7 +732,10 @@ def main():
         # the product driver itself: the C++ step loop (cabanamd_b200/host, binary cbnMD) on configs[0]
         # (input/in.lj as shipped: 20^3 fcc cells) and on the headline workload — no Python in the loop
         for cells, steps in ((20, 2000), (args.cells, 200)):
-            r = cbnmd_leg(cells, steps)
+            try:
+                r = cbnmd_leg(cells, steps)
+            except Exception as e:  # noqa: BLE001 - an extra leg must never take the bench line down
+                r = {"error": repr(e)[:300]}
             if r:
                 extra[f"cbnMD (C++ driver) in.lj, {4 * cells ** 3} atoms, {steps} steps"] = r
     if not args.no_extra:
