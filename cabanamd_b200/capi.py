@@ -82,6 +82,7 @@ def load_library():
     L.cbmd_energy_lj.argtypes = [vp, C.c_int, c_dp, c_dp]
     L.cbmd_virial_lj.argtypes = [vp, C.c_int, c_dp]
     L.cbmd_request_energy.argtypes = [vp]
+    L.cbmd_md_steps.argtypes = [vp, C.c_int, C.c_int]
     L.cbmd_comm_unique_id.argtypes = [vp]
     L.cbmd_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.cbmd_comm_rank.argtypes = [vp, c_ip, c_ip]
@@ -317,6 +318,10 @@ class Context:
         a = C.c_double()
         self._ck(self.L.cbmd_virial_lj(self.h, int(self.half if half is None else half), C.byref(a)))
         return a.value
+
+    def md_steps(self, nsteps, half=False):
+        """nsteps plain MD steps (no rebuild, no thermo) in one call; graph replay on one rank."""
+        self._ck(self.L.cbmd_md_steps(self.h, int(nsteps), int(half)))
 
     # ---- Comm
     @staticmethod

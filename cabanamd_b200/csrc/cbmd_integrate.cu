@@ -75,6 +75,7 @@ void cbmd_materialize_final( cbmd_ctx *ctx )
     if ( !ctx->final_pending )
         return;
     ctx->final_pending = false;
+    ctx->v_epoch++;
     TimedRegion timed__( ctx, CBMD_T_INTEGRATE );
     const int n = ctx->n_local;
     if ( n > 0 )
@@ -248,6 +249,11 @@ extern "C" int cbmd_sum_mv2( cbmd_ctx *ctx, double *sum )
         *sum = 0.0;
         return 0;
     }
+    if ( ctx->mv2_epoch == ctx->v_epoch ) // Temperature and KinE ask for the same sum (property_*.h)
+    {
+        *sum = ctx->mv2_cached;
+        return 0;
+    }
     int nblk = div_up( n, 256 );
     if ( nblk > 1184 )
         nblk = 1184; // 148 SMs x 8 resident CTAs
@@ -258,5 +264,7 @@ extern "C" int cbmd_sum_mv2( cbmd_ctx *ctx, double *sum )
                                 cudaMemcpyDeviceToHost, ctx->stream ) );
     CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );
     *sum = ctx->h_pinned[0];
+    ctx->mv2_cached = *sum;
+    ctx->mv2_epoch = ctx->v_epoch;
     CBMD_API_END
 }

@@ -164,6 +164,14 @@ struct cbmd_ctx
     // validates the pair energy cached by a fused force+energy sweep
     uint64_t epoch = 1;
     bool energy_hint = false, pe_valid = false;
+    // thermo output (three blocking reads per thermo step in the reference's order: T, PE, KE) costs one
+    // host synchronisation instead of three: the fused sweep's energy is copied to pinned host memory
+    // behind the sweep (ev_pe marks it; by the time PotE asks, the Temperature read has drained the
+    // stream), and sum(m v^2) is cached until a call changes the velocities (v_epoch)
+    cudaEvent_t ev_pe = nullptr;
+    uint64_t pe_host_epoch = 0;
+    uint64_t v_epoch = 1, mv2_epoch = 0;
+    double mv2_cached = 0.0;
     uint64_t pe_epoch = 0;
     int pe_half = 0;
     double *pe_partial = nullptr;
@@ -265,12 +273,18 @@ struct cbmd_ctx
 
     bool nvtx = false; // option "nvtx" / CBMD_NVTX=1: NVTX range per timed region (Force, Neigh, Comm, ...)
     // CUDA-event timers (cbmd_timing_*)
+    // cbmd_md_steps (cbmd_steps.cu): plain steps replayed from a CUDA graph
+    int graph_steps = 1; // option "graph_steps"
+    cudaGraphExec_t step_graph_exec = nullptr;
+    int64_t graph_launches = 0;
     bool timing = false;
+    int timing_stride = 7; // option "timing_stride": 1 = every region timed
     struct Bucket
     {
         std::vector<cudaEvent_t> pending; // start,end,start,end,...
-        double ms = 0.0;
-        int64_t count = 0;
+        double ms = 0.0;    // device time of the SAMPLED regions
+        int64_t count = 0;  // sampled regions folded into ms
+        int64_t calls = 0;  // all regions entered while timing was on
     } bucket[CBMD_T_NBUCKETS];
     std::vector<cudaEvent_t> event_pool;
 };
@@ -306,6 +320,15 @@ struct TimedRegion
             ranged = true;
         }
         if ( !ctx->timing )
+            return;
+        // A timing event costs the host a record and the device a timestamp between two kernels:
+        // about 2.8 us each, ten per MD step — more than the kernels of a 32 000-atom step take
+        // (scripts/small_system_breakdown.py: 26.6 -> 54.4 us per plain step).  Every region of a
+        // bucket is timed for its first 16 calls, afterwards one in 7 (coprime with the 10- and
+        // 20-step periods of thermo output and rebuilds); cbmd_timing_get scales the sampled time
+        // to all calls.
+        const int64_t call = ctx->bucket[b].calls++;
+        if ( ctx->timing_stride > 1 && call >= 16 && call % ctx->timing_stride != 0 )
             return;
         cudaEvent_t e0 = get( ctx );
         e1 = get( ctx );
@@ -417,6 +440,7 @@ inline int64_t div_up64( int64_t a, int64_t b ) { return ( a + b - 1 ) / b; }
 // internal host helpers implemented across the .cu files
 void cbmd_ensure_capacity( cbmd_ctx *ctx, int n );
 void cbmd_hub_detach( cbmd_ctx *ctx ); // cbmd_comm.cu
+void cbmd_graph_release( cbmd_ctx *ctx ); // cbmd_steps.cu
 inline void cbmd_join_halo( cbmd_ctx *ctx )
 {
     if ( ctx->halo_pending )
@@ -436,6 +460,8 @@ inline void cbmd_bump_epoch( cbmd_ctx *ctx, bool owned_changed, bool ghosts_chan
     const bool o = ctx->mirror_owned_epoch == ctx->epoch && !owned_changed;
     const bool g = ctx->mirror_ghost_epoch == ctx->epoch && !ghosts_changed;
     ctx->epoch++;
+    if ( owned_changed )
+        ctx->v_epoch++; // integrator, migration, sort, upload: the owned velocities (or their set) changed
     if ( o )
         ctx->mirror_owned_epoch = ctx->epoch;
     if ( g )

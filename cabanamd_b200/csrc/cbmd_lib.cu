@@ -6,3 +6,4 @@
 #include "cbmd_neighbor.cu"
 #include "cbmd_force.cu"
 #include "cbmd_comm.cu"
+#include "cbmd_steps.cu"

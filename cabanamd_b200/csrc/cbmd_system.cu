@@ -230,6 +230,8 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
             ctx->overlap = atoi( e );
         if ( const char *e = getenv( "CBMD_HALO_STAGES" ) ) // A/B switch: 3 = per-dimension forwarding
             ctx->halo_stages = atoi( e ) == 3 ? 3 : 1;
+        if ( const char *e = getenv( "CBMD_GRAPH" ) ) // A/B switch: 0 = cbmd_md_steps issues every step launch by launch
+            ctx->graph_steps = atoi( e ) != 0;
         if ( const char *e = getenv( "CBMD_EARLY" ) ) // A/B switch: 1 = refresh overlaps the integrator, one force launch
             ctx->early_integrate = atoi( e ) != 0;
         if ( const char *e = getenv( "CBMD_GATHER" ) ) // A/B switch: 0 = 32-byte records by LDG.256
@@ -247,6 +249,7 @@ extern "C" int cbmd_create( cbmd_ctx **out, int device )
             int lo = 0, hi = 0; // comm stream gets the highest priority so its small kernels
             CBMD_CUDA( cudaDeviceGetStreamPriorityRange( &lo, &hi ) ); // slip in between force CTAs
             CBMD_CUDA( cudaStreamCreateWithPriority( &ctx->comm_stream, cudaStreamNonBlocking, hi ) );
+            CBMD_CUDA( cudaEventCreateWithFlags( &ctx->ev_pe, cudaEventDisableTiming ) );
             CBMD_CUDA( cudaEventCreateWithFlags( &ctx->ev_x, cudaEventDisableTiming ) );
             CBMD_CUDA( cudaEventCreateWithFlags( &ctx->ev_halo, cudaEventDisableTiming ) );
             CBMD_CUDA( cudaStreamCreateWithFlags( &ctx->aux_stream, cudaStreamNonBlocking ) );
@@ -282,11 +285,13 @@ extern "C" int cbmd_destroy( cbmd_ctx *ctx )
     cudaSetDevice( ctx->device );
     cudaStreamSynchronize( ctx->stream );
     cbmd_hub_detach( ctx );
+    cbmd_graph_release( ctx );
     if ( ctx->comm_stream )
     {
         cudaStreamSynchronize( ctx->comm_stream );
         cudaStreamDestroy( ctx->comm_stream );
         cudaEventDestroy( ctx->ev_x );
+        cudaEventDestroy( ctx->ev_pe );
         cudaEventDestroy( ctx->ev_halo );
         cudaStreamSynchronize( ctx->aux_stream );
         cudaStreamDestroy( ctx->aux_stream );
@@ -347,6 +352,14 @@ extern "C" int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value )
         ctx->overlap = (int)value;
     else if ( n == "nvtx" )
         ctx->nvtx = value != 0.0;
+    else if ( n == "graph_steps" )
+        ctx->graph_steps = value != 0.0;
+    else if ( n == "timing_stride" )
+    {
+        if ( value < 1.0 )
+            throw CbmdError( "timing_stride must be >= 1" );
+        ctx->timing_stride = (int)value;
+    }
     else if ( n == "early_integrate" )
     {
         // multi-rank step with the one-stage refresh: 0 (default) = the exchange runs beside the interior
@@ -442,10 +455,11 @@ extern "C" int cbmd_timing_get( cbmd_ctx *ctx, int bucket, double *ms, int64_t *
     CBMD_API_BEGIN
     CBMD_REQUIRE( bucket >= 0 && bucket < CBMD_T_NBUCKETS, "bad timing bucket" );
     timing_drain( ctx );
-    if ( ms )
-        *ms = ctx->bucket[bucket].ms;
+    const auto &B = ctx->bucket[bucket];
+    if ( ms ) // sampled device time scaled to all regions of the bucket
+        *ms = B.count > 0 ? B.ms * ( (double)B.calls / (double)B.count ) : 0.0;
     if ( count )
-        *count = ctx->bucket[bucket].count;
+        *count = B.calls;
     CBMD_API_END
 }
 
@@ -457,6 +471,7 @@ extern "C" int cbmd_timing_reset( cbmd_ctx *ctx )
     {
         ctx->bucket[b].ms = 0.0;
         ctx->bucket[b].count = 0;
+        ctx->bucket[b].calls = 0;
     }
     CBMD_API_END
 }
@@ -488,6 +503,7 @@ extern "C" int cbmd_set_mass( cbmd_ctx *ctx, int ntypes, const double *mass )
     for ( int t = 0; t < ntypes; t++ )
         ctx->mass.mass[t] = mass[t];
     refresh_dtfm( ctx );
+    ctx->v_epoch++; // sum(m v^2) changes with the masses
     CBMD_API_END
 }
 
@@ -628,6 +644,7 @@ extern "C" int cbmd_set_velocities( cbmd_ctx *ctx, int n_local, const double *v 
         CBMD_LAUNCH_CHECK( ctx );
         CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );
     }
+    ctx->v_epoch++;
     CBMD_API_END
 }
 

@@ -89,9 +89,22 @@ class Simulation:
         self.step = 0
 
     # cabanamd_impl.h:285-399 (one step)
-    def run(self, nsteps, thermo_rate=0):
+    def _special(self, step, thermo_rate):
+        return step % self.exchange_rate == 0 or bool(thermo_rate and step % thermo_rate == 0)
+
+    def run(self, nsteps, thermo_rate=0, batch=True):
+        """batch: stretches of plain steps (no rebuild, no thermo) go through ONE C-ABI call
+        (cbmd_md_steps: the same entry points in the same order inside the library)."""
         c = self.ctx
-        for _ in range(nsteps):
+        end = self.step + nsteps
+        while self.step < end:
+            if batch and not self._special(self.step + 1, thermo_rate):
+                k = 1
+                while self.step + k < end and not self._special(self.step + k + 1, thermo_rate):
+                    k += 1
+                c.md_steps(k, self.half)
+                self.step += k
+                continue
             self.step += 1
             c.integrate_initial()
             if self.step % self.exchange_rate == 0:

@@ -5,6 +5,7 @@
 #define CBMD_HOST_CABANAMD_H
 
 #include <chrono>
+#include <cstdlib>
 #include <fstream>
 #include <iomanip>
 #include <memory>
@@ -170,8 +171,30 @@ class CbnMD : public CabanaMD
         auto seconds = [&] { return std::chrono::duration<double>( clock::now() - t0 ).count(); };
         double last_time = 0;
 
+        // steps with nothing but the six module calls (no rebuild, no thermo line, no dump) are handed to
+        // the library in stretches: cbmd_md_steps makes the same calls in the same order and, on one rank,
+        // replays them from a CUDA graph (a step of in.lj as shipped is launch-bound otherwise).
+        // CBMD_BATCH_STEPS=0 keeps every step in this loop.
+        const char *be = std::getenv( "CBMD_BATCH_STEPS" );
+        const bool batch_plain = !( be && std::atoi( be ) == 0 );
+        auto due = []( bool on, int rate, int s ) { return on && rate > 0 && s % rate == 0; };
+        auto special = [&]( int s ) {
+            return s % input->comm_exchange_rate == 0 || due( true, thermo_rate, s ) ||
+                   due( true, input->vtk_rate, s ) || due( input->dumpbinaryflag, input->dumpbinary_rate, s ) ||
+                   due( input->correctnessflag, input->correctness_rate, s );
+        };
+
         for ( int step = 1; step <= nsteps; step++ )
         {
+            if ( batch_plain && !special( step ) )
+            {
+                int k = 1;
+                while ( step + k <= nsteps && !special( step + k ) )
+                    k++;
+                cbmd_check( cbmd_md_steps( system->ctx, k, half_neigh ? 1 : 0 ), "cbmd_md_steps" );
+                step += k - 1;
+                continue;
+            }
             integrator->initial_integrate( system );
 
             if ( step % input->comm_exchange_rate == 0 && step > 0 )

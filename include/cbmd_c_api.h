@@ -126,6 +126,15 @@ extern "C"
      * rebuilt the list in between (otherwise it runs its own sweep, as without the hint). */
     int cbmd_request_energy( cbmd_ctx *ctx );
 
+    /* ---- a run of plain steps (cabanamd_impl.h:285-399 between two rebuild / thermo steps) ---- */
+    /* nsteps times: cbmd_integrate_initial, cbmd_update_halo, cbmd_zero_force, cbmd_force_lj( half ),
+     * cbmd_update_force (half lists), cbmd_integrate_final — the same entry points in the same order,
+     * so the result is bit-identical to calling them one by one.  On one rank the steps after the
+     * first are replayed from a CUDA graph captured from those very calls (option "graph_steps"):
+     * a step of input/in.lj (32 000 atoms) is launch-bound otherwise.  The caller keeps rebuild
+     * steps (cbmd_exchange ... cbmd_neigh_build) and thermo steps (cbmd_request_energy) outside. */
+    int cbmd_md_steps( cbmd_ctx *ctx, int nsteps, int half );
+
     /* ---- Comm (comm_mpi.h:125-138, comm_mpi_impl.h) ----------------------------- */
     /* 128-byte NCCL unique id created on rank 0 and handed to every rank out of band */
     int cbmd_comm_unique_id( void *id128 );
@@ -217,6 +226,11 @@ extern "C"
      *               (round 1).  Same sets.
      *   "halo_stages" 1 (default) multi-rank ghost refresh straight from the root ranks in one NCCL
      *               group; 3 = the reference's forwarding scheme, one group per dimension
+     *   "graph_steps" 1 (default) cbmd_md_steps replays its steps from a CUDA graph (one rank); 0 = launch
+     *               by launch
+     *   "timing_stride" 7 (default) the CUDA-event timers of cbmd_timing_* time every region of a bucket
+     *               for its first 16 calls and one in 7 afterwards, and scale to all calls (an event pair
+     *               per region costs more than the kernels of a small system take); 1 = time every region
      *   "nvtx"      1 = NVTX ranges (cbmd:Force, cbmd:Neigh, cbmd:Comm, ...) around the entry points
      *   "overlap"   1 (default) multi-rank halo refresh on a second stream beside other work, 0 = in line
      *   "early_integrate" 0 (default) the one-stage refresh runs beside the interior tiles of a split
@@ -224,7 +238,7 @@ extern "C"
      *               runs beside the integration of the interior tiles and the force sweep is one launch
      *               (+0.6 % at N=2 with 4 M atoms per GPU; the window shrinks with the atoms per GPU)
      * Environment overrides read at cbmd_create: CBMD_GATHER, CBMD_PRECISION, CBMD_NEIGH_KERNEL,
-     * CBMD_ROW_ORDER, CBMD_HALF_KERNEL, CBMD_HALO_STAGES, CBMD_OVERLAP, CBMD_EARLY. */
+     * CBMD_ROW_ORDER, CBMD_HALF_KERNEL, CBMD_HALO_STAGES, CBMD_OVERLAP, CBMD_EARLY, CBMD_GRAPH. */
     int cbmd_set_option( cbmd_ctx *ctx, const char *name, double value );
 
 #ifdef __cplusplus

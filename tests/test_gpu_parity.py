@@ -499,6 +499,38 @@ def test_trajectory_and_thermo_match_oracle(cb, half):
     assert np.abs(xa - xo).max() < 1e-8
 
 
+@pytest.mark.parametrize("half", [False, True])
+def test_batched_plain_steps_are_bit_identical_to_stepwise(cb, half):
+    """cbmd_md_steps (stretches of plain steps in one call, replayed from a CUDA graph on one rank) against
+    the six module calls per step: same kernels, arguments and order, so x, v, f and the thermo trace are
+    bit-identical — with the graph (default) and without it (option graph_steps 0)."""
+    from cabanamd_b200.harness import Simulation
+
+    s0 = O.Sim(mass=[2.0], half=half).create_lattice_fcc(cells=(8, 8, 8))
+    d, dom = s0.get(), s0.domain()
+    runs = []
+    for mode in ("stepwise", "graph", "nograph"):
+        sim = Simulation(half=half)
+        if mode == "nograph":
+            sim.ctx.set_option("graph_steps", 0)
+        sim.set_box(dom["llo"], dom["lhi"])
+        sim.set_atoms(d["x"], d["v"], d["type"], d["id"])
+        sim.setup()
+        sim.record_thermo()
+        l0 = sim.ctx.launch_count()
+        sim.run(67, 10, batch=(mode != "stepwise"))  # ends inside a stretch, 3 rebuilds, 6 thermo steps
+        a = sim.ctx.get_atoms()
+        runs.append((a, np.array(sim.thermo), sim.ctx.launch_count() - l0))
+        sim.ctx.close()
+    ref = runs[0]
+    for a, th, _ in runs[1:]:
+        assert np.array_equal(th, ref[1])
+        for k in ("x", "v", "f", "id"):
+            assert np.array_equal(a[k], ref[0][k]), k
+    # the replayed steps are counted as the launches they contain
+    assert runs[1][2] == runs[2][2] == runs[0][2]
+
+
 def test_inlj_step0_known_answer_gpu(cb):
     """T5: in.lj (256 000 atoms) step-0 thermo: 1.400000 / -6.332812 / -4.232820."""
     from cabanamd_b200.harness import Simulation, fcc_lattice
