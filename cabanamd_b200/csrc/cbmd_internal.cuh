@@ -278,13 +278,18 @@ struct cbmd_ctx
     cudaGraphExec_t step_graph_exec = nullptr;
     int64_t graph_launches = 0;
     bool timing = false;
-    int timing_stride = 7; // option "timing_stride": 1 = every region timed
+    int timing_stride = 7; // option "timing_stride": one plain step in this many is timed (1 = all)
+    int timing_mode = 0;   // 0 = time the region; 1 / 2 = region of a sampled / unsampled plain step
+    int64_t plain_seen = 0; // plain steps since timing was switched on or reset
     struct Bucket
     {
-        std::vector<cudaEvent_t> pending; // start,end,start,end,...
-        double ms = 0.0;    // device time of the SAMPLED regions
-        int64_t count = 0;  // sampled regions folded into ms
-        int64_t calls = 0;  // all regions entered while timing was on
+        // two classes of regions: [0] timed every time (everything outside cbmd_md_steps: rebuild and
+        // thermo steps, set-up); [1] regions of the plain steps inside cbmd_md_steps, of which only a
+        // sample is timed (timing_mode 1) and the rest only counted (timing_mode 2, graph replays)
+        std::vector<cudaEvent_t> pending[2]; // start,end,start,end,...
+        double ms[2] = { 0.0, 0.0 };         // device time of the timed regions
+        int64_t count[2] = { 0, 0 };         // timed regions folded into ms
+        int64_t calls[2] = { 0, 0 };         // regions entered while timing was on
     } bucket[CBMD_T_NBUCKETS];
     std::vector<cudaEvent_t> event_pool;
 };
@@ -294,6 +299,7 @@ struct TimedRegion
 {
     cbmd_ctx *ctx;
     int b;
+    int cls = 0;
     cudaEvent_t e1 = nullptr;
     static cudaEvent_t get( cbmd_ctx *c )
     {
@@ -323,17 +329,17 @@ struct TimedRegion
             return;
         // A timing event costs the host a record and the device a timestamp between two kernels:
         // about 2.8 us each, ten per MD step — more than the kernels of a 32 000-atom step take
-        // (scripts/small_system_breakdown.py: 26.6 -> 54.4 us per plain step).  Every region of a
-        // bucket is timed for its first 16 calls, afterwards one in 7 (coprime with the 10- and
-        // 20-step periods of thermo output and rebuilds); cbmd_timing_get scales the sampled time
-        // to all calls.
-        const int64_t call = ctx->bucket[b].calls++;
-        if ( ctx->timing_stride > 1 && call >= 16 && call % ctx->timing_stride != 0 )
+        // (profiles/r2_small_system_breakdown.txt).  Regions of the plain steps inside cbmd_md_steps
+        // are therefore SAMPLED (the first 16 plain steps, then one in timing_stride) and
+        // cbmd_timing_get scales their time to all plain steps; everything else is timed every time.
+        cls = ctx->timing_mode == 0 ? 0 : 1;
+        ctx->bucket[b].calls[cls]++;
+        if ( ctx->timing_mode == 2 )
             return;
         cudaEvent_t e0 = get( ctx );
         e1 = get( ctx );
         cudaEventRecord( e0, ctx->stream );
-        ctx->bucket[b].pending.push_back( e0 );
+        ctx->bucket[b].pending[cls].push_back( e0 );
     }
     ~TimedRegion()
     {
@@ -343,25 +349,26 @@ struct TimedRegion
             return;
         cudaEventRecord( e1, ctx->stream );
         auto &B = ctx->bucket[b];
-        B.pending.push_back( e1 );
+        auto &P = B.pending[cls];
+        P.push_back( e1 );
         // long runs: fold the pairs that have already completed into the totals (no stall) so the
         // number of live events stays bounded
-        if ( B.pending.size() >= 1024 )
+        if ( P.size() >= 1024 )
         {
             size_t k = 0;
-            while ( k + 1 < B.pending.size() && cudaEventQuery( B.pending[k + 1] ) == cudaSuccess )
+            while ( k + 1 < P.size() && cudaEventQuery( P[k + 1] ) == cudaSuccess )
             {
                 float ms = 0.f;
-                if ( cudaEventElapsedTime( &ms, B.pending[k], B.pending[k + 1] ) == cudaSuccess )
+                if ( cudaEventElapsedTime( &ms, P[k], P[k + 1] ) == cudaSuccess )
                 {
-                    B.ms += ms;
-                    B.count++;
+                    B.ms[cls] += ms;
+                    B.count[cls]++;
                 }
-                ctx->event_pool.push_back( B.pending[k] );
-                ctx->event_pool.push_back( B.pending[k + 1] );
+                ctx->event_pool.push_back( P[k] );
+                ctx->event_pool.push_back( P[k + 1] );
                 k += 2;
             }
-            B.pending.erase( B.pending.begin(), B.pending.begin() + k );
+            P.erase( P.begin(), P.begin() + k );
             (void)cudaGetLastError(); // a "not ready" from the last query is not an error
         }
     }

@@ -36,24 +36,34 @@ void cbmd_graph_release( cbmd_ctx *ctx )
 }
 
 // capture one plain step on the context stream; returns the graph or nullptr (the caller then
-// falls back to the entry points; a failed capture leaves no work behind)
-static cudaGraph_t capture_step( cbmd_ctx *ctx, int half, int64_t *launches )
+// falls back to the entry points; a failed capture leaves no work behind).  The regions of the
+// captured step are counted as unsampled plain-step regions (timing_mode 2: event pairs inside a
+// graph could not be read back); calls[b] receives how many regions of bucket b one step has.
+static cudaGraph_t capture_step( cbmd_ctx *ctx, int half, int64_t *launches, int64_t calls[CBMD_T_NBUCKETS] )
 {
-    const bool timing = ctx->timing;
-    ctx->timing = false; // event pairs inside a graph cannot be read back; see cbmd_md_steps
     const int64_t before = ctx->launches;
+    for ( int b = 0; b < CBMD_T_NBUCKETS; b++ )
+        calls[b] = ctx->bucket[b].calls[1];
     cudaGraph_t graph = nullptr;
     if ( cudaStreamBeginCapture( ctx->stream, cudaStreamCaptureModeThreadLocal ) != cudaSuccess )
     {
         (void)cudaGetLastError();
-        ctx->timing = timing;
         return nullptr;
     }
+    ctx->timing_mode = 2;
     const int rc = plain_step( ctx, half );
+    ctx->timing_mode = 0;
     const cudaError_t e = cudaStreamEndCapture( ctx->stream, &graph );
-    ctx->timing = timing;
+    // the capture ran the host side of one step without running the step: its launches and regions are
+    // counted when (and as often as) the graph is launched
     *launches = ctx->launches - before;
-    ctx->launches = before; // counted when the graph is launched
+    ctx->launches = before;
+    for ( int b = 0; b < CBMD_T_NBUCKETS; b++ )
+    {
+        const int64_t d = ctx->bucket[b].calls[1] - calls[b];
+        ctx->bucket[b].calls[1] -= d;
+        calls[b] = d;
+    }
     if ( rc != 0 || e != cudaSuccess || graph == nullptr )
     {
         (void)cudaGetLastError();
@@ -64,71 +74,80 @@ static cudaGraph_t capture_step( cbmd_ctx *ctx, int half, int64_t *launches )
     return graph;
 }
 
+// one plain step through the entry points, its regions sampled (mode 1) or only counted (mode 2)
+static int eager_step( cbmd_ctx *ctx, int half, int mode )
+{
+    ctx->timing_mode = mode;
+    const int rc = plain_step( ctx, half );
+    ctx->timing_mode = 0;
+    return rc;
+}
+
 extern "C" int cbmd_md_steps( cbmd_ctx *ctx, int nsteps, int half )
 {
     CBMD_API_BEGIN_NOJOIN
     CBMD_REQUIRE( nsteps >= 0, "negative step count" );
-    const bool graphable = ctx->graph_steps && ctx->nranks == 1 && !ctx->nvtx && nsteps >= 4;
-    int done = 0;
-    if ( graphable )
+    const bool graphable = ctx->graph_steps && ctx->nranks == 1 && !ctx->nvtx;
+    bool have_graph = false, tried = false;
+    int64_t per_step = 0, calls[CBMD_T_NBUCKETS] = { 0 };
+    for ( int done = 0; done < nsteps; done++ )
     {
-        // step 1: the ordinary way (it also settles every lazy allocation the step needs)
-        if ( plain_step( ctx, half ) != 0 )
-            return 1;
-        done = 1;
-        // the state a captured step starts from must be the state it ends in, or replaying it would
-        // not be the same as calling the entry points again: the list and the ghost plan are current,
-        // a final_integrate is pending (fused into the next initial_integrate), nothing else is lazy
-        const bool steady = ctx->final_pending && !ctx->halo_pending && !ctx->energy_hint && ctx->flat_halo_ok;
-        int64_t per_step = 0;
-        cudaGraph_t graph = steady ? capture_step( ctx, half, &per_step ) : nullptr;
-        if ( graph )
+        // timers: the first 16 plain steps and one in timing_stride afterwards are timed, through the
+        // entry points; the others only count their regions (cbmd_timing_get scales)
+        const bool sample = ctx->timing && ( ctx->plain_seen < 16 || ctx->plain_seen % ctx->timing_stride == 0 );
+        ctx->plain_seen++;
+        if ( sample || !graphable || done == 0 )
         {
-            bool ok = true;
-            if ( ctx->step_graph_exec )
+            // (the first step of a stretch always runs the ordinary way: it settles every lazy
+            // allocation and re-split a rebuild step may have left behind)
+            if ( eager_step( ctx, half, sample ? 1 : 2 ) != 0 )
+                return 1;
+            continue;
+        }
+        if ( !tried && nsteps - done >= 2 )
+        {
+            tried = true;
+            // the state a captured step starts from must be the state it ends in, or replaying it would
+            // not be the same as calling the entry points again: the list and the ghost plan are current,
+            // a final_integrate is pending (fused into the next initial_integrate), nothing else is lazy
+            const bool steady = ctx->final_pending && !ctx->halo_pending && !ctx->energy_hint && ctx->flat_halo_ok;
+            cudaGraph_t graph = steady ? capture_step( ctx, half, &per_step, calls ) : nullptr;
+            if ( graph )
             {
-                cudaGraphExecUpdateResultInfo info;
-                if ( cudaGraphExecUpdate( ctx->step_graph_exec, graph, &info ) != cudaSuccess )
+                if ( ctx->step_graph_exec )
+                {
+                    cudaGraphExecUpdateResultInfo info;
+                    if ( cudaGraphExecUpdate( ctx->step_graph_exec, graph, &info ) != cudaSuccess )
+                    {
+                        (void)cudaGetLastError();
+                        cbmd_graph_release( ctx );
+                    }
+                }
+                if ( !ctx->step_graph_exec &&
+                     cudaGraphInstantiate( &ctx->step_graph_exec, graph, 0 ) != cudaSuccess )
                 {
                     (void)cudaGetLastError();
-                    cbmd_graph_release( ctx );
+                    ctx->step_graph_exec = nullptr;
                 }
+                cudaGraphDestroy( graph );
+                have_graph = ctx->step_graph_exec != nullptr;
+                // The capture has advanced the host-side bookkeeping (epochs, lazy flags) by one step
+                // without running it.  Every cache keyed by the epochs compares for equality with the
+                // CURRENT epoch, so the state is that of a step through the entry points whether the
+                // step is now run from the graph or (no graph) once more through the entry points.
             }
-            if ( !ctx->step_graph_exec &&
-                 cudaGraphInstantiate( &ctx->step_graph_exec, graph, 0 ) != cudaSuccess )
-            {
-                (void)cudaGetLastError();
-                ctx->step_graph_exec = nullptr;
-                ok = false;
-            }
-            cudaGraphDestroy( graph );
-            // the capture has advanced the host-side bookkeeping (epochs, lazy flags) by one step without
-            // running it: the graph launches below are that step and the ones after it
-            for ( ; ok && done < nsteps; done++ )
-            {
-                CBMD_CUDA( cudaGraphLaunch( ctx->step_graph_exec, ctx->stream ) );
-                ctx->launches += per_step;
-                ctx->graph_launches++;
-                if ( ctx->timing ) // unsampled calls of the per-step buckets (cbmd_timing_get scales)
-                    for ( int b : { CBMD_T_FORCE, CBMD_T_FORCE_KERNEL, CBMD_T_COMM, CBMD_T_INTEGRATE } )
-                        ctx->bucket[b].calls++;
-            }
-            if ( !ok )
-            {
-                // the captured step never ran, yet its bookkeeping did: positions and velocities are one
-                // step behind only in the sense that the step still has to be executed — do it now
-                if ( plain_step( ctx, half ) != 0 )
-                    return 1;
-                done++;
-            }
-            // no further bookkeeping: every cache keyed by the epochs compares for equality with the
-            // CURRENT epoch, and the captured step has left them exactly as a step through the entry
-            // points does (mirror parts current if the step keeps them current, energy cache invalid,
-            // sum(m v^2) cache invalid); replaying the step does not change which of them hold
         }
-    }
-    for ( ; done < nsteps; done++ )
-        if ( plain_step( ctx, half ) != 0 )
+        if ( have_graph )
+        {
+            CBMD_CUDA( cudaGraphLaunch( ctx->step_graph_exec, ctx->stream ) );
+            ctx->launches += per_step;
+            ctx->graph_launches++;
+            if ( ctx->timing )
+                for ( int b = 0; b < CBMD_T_NBUCKETS; b++ )
+                    ctx->bucket[b].calls[1] += calls[b];
+        }
+        else if ( eager_step( ctx, half, 2 ) != 0 )
             return 1;
+    }
     CBMD_API_END
 }

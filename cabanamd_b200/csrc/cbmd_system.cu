@@ -325,8 +325,9 @@ extern "C" int cbmd_destroy( cbmd_ctx *ctx )
     if ( ctx->nccl )
         ncclCommDestroy( ctx->nccl );
     for ( int b = 0; b < CBMD_T_NBUCKETS; b++ )
-        for ( cudaEvent_t e : ctx->bucket[b].pending )
-            cudaEventDestroy( e );
+        for ( int c = 0; c < 2; c++ )
+            for ( cudaEvent_t e : ctx->bucket[b].pending[c] )
+                cudaEventDestroy( e );
     for ( cudaEvent_t e : ctx->event_pool )
         cudaEventDestroy( e );
     cudaStreamDestroy( ctx->stream );
@@ -426,19 +427,21 @@ static void timing_drain( cbmd_ctx *ctx )
 {
     CBMD_CUDA( cudaStreamSynchronize( ctx->stream ) );
     for ( int b = 0; b < CBMD_T_NBUCKETS; b++ )
-    {
-        auto &B = ctx->bucket[b];
-        for ( size_t k = 0; k + 1 < B.pending.size(); k += 2 )
+        for ( int c = 0; c < 2; c++ )
         {
-            float ms = 0.f;
-            CBMD_CUDA( cudaEventElapsedTime( &ms, B.pending[k], B.pending[k + 1] ) );
-            B.ms += ms;
-            B.count++;
-            ctx->event_pool.push_back( B.pending[k] );
-            ctx->event_pool.push_back( B.pending[k + 1] );
+            auto &B = ctx->bucket[b];
+            auto &P = B.pending[c];
+            for ( size_t k = 0; k + 1 < P.size(); k += 2 )
+            {
+                float ms = 0.f;
+                CBMD_CUDA( cudaEventElapsedTime( &ms, P[k], P[k + 1] ) );
+                B.ms[c] += ms;
+                B.count[c]++;
+                ctx->event_pool.push_back( P[k] );
+                ctx->event_pool.push_back( P[k + 1] );
+            }
+            P.clear();
         }
-        B.pending.clear();
-    }
 }
 
 extern "C" int cbmd_timing_enable( cbmd_ctx *ctx, int on )
@@ -446,6 +449,8 @@ extern "C" int cbmd_timing_enable( cbmd_ctx *ctx, int on )
     CBMD_API_BEGIN
     if ( !on )
         timing_drain( ctx );
+    else if ( !ctx->timing )
+        ctx->plain_seen = 0;
     ctx->timing = on != 0;
     CBMD_API_END
 }
@@ -456,10 +461,10 @@ extern "C" int cbmd_timing_get( cbmd_ctx *ctx, int bucket, double *ms, int64_t *
     CBMD_REQUIRE( bucket >= 0 && bucket < CBMD_T_NBUCKETS, "bad timing bucket" );
     timing_drain( ctx );
     const auto &B = ctx->bucket[bucket];
-    if ( ms ) // sampled device time scaled to all regions of the bucket
-        *ms = B.count > 0 ? B.ms * ( (double)B.calls / (double)B.count ) : 0.0;
+    if ( ms ) // regions timed every time + the sampled plain-step regions scaled to all plain steps
+        *ms = B.ms[0] + ( B.count[1] > 0 ? B.ms[1] * ( (double)B.calls[1] / (double)B.count[1] ) : 0.0 );
     if ( count )
-        *count = B.calls;
+        *count = B.calls[0] + B.calls[1];
     CBMD_API_END
 }
 
@@ -468,11 +473,13 @@ extern "C" int cbmd_timing_reset( cbmd_ctx *ctx )
     CBMD_API_BEGIN
     timing_drain( ctx );
     for ( int b = 0; b < CBMD_T_NBUCKETS; b++ )
-    {
-        ctx->bucket[b].ms = 0.0;
-        ctx->bucket[b].count = 0;
-        ctx->bucket[b].calls = 0;
-    }
+        for ( int c = 0; c < 2; c++ )
+        {
+            ctx->bucket[b].ms[c] = 0.0;
+            ctx->bucket[b].count[c] = 0;
+            ctx->bucket[b].calls[c] = 0;
+        }
+    ctx->plain_seen = 0;
     CBMD_API_END
 }
 
