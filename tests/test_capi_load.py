@@ -84,3 +84,68 @@ def test_verlet_table_addressing(rows):
         assert off[0, n] % 128 == n % 4
         if n % 4:
             assert np.array_equal(off[:, n], off[:, n - 1] + 1)
+
+
+def test_hub_objects_are_host_side_and_checked():
+    """cbmd_hub_create / cbmd_hub_destroy need no device: creation, argument checks, destruction."""
+    h = cb.Hub(4, timeout=1.0)
+    assert h.nranks == 4
+    h.close()
+    h.close()  # idempotent
+    with pytest.raises(cb.CbmdError, match="nranks"):
+        cb.Hub(0)
+    with pytest.raises(cb.CbmdError, match="nranks"):
+        cb.Hub(65)
+
+
+class _Recorder:
+    """Stands in for capi.Context: records the module calls of the step loop."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        def f(*a, **k):
+            self.calls.append((name,) + tuple(a))
+            return {"neigh_build": 50, "sum_mv2": 1.0, "reduce_sum": 1.0, "energy": (0.0, 0.0)}.get(name, 0)
+
+        return f
+
+
+def _expand(calls, half):
+    """cbmd_md_steps(n, half) = n times the six module calls (include/cbmd_c_api.h)."""
+    out = []
+    for c in calls:
+        if c[0] == "md_steps":
+            step = [("integrate_initial",), ("update_halo",), ("zero_force",), ("force", half)]
+            step += [("update_force",)] if half else []
+            step += [("integrate_final",)]
+            out += step * c[1]
+        else:
+            out.append(c)
+    return out
+
+
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("nsteps,thermo", [(67, 10), (45, 0), (20, 1), (19, 7), (1, 0), (40, 20)])
+def test_step_loop_batching_keeps_the_call_sequence(nsteps, thermo, half):
+    """harness.Simulation.run hands stretches of plain steps to cbmd_md_steps; expanded, the sequence of
+    module calls is exactly the stepwise one (the order of CbnMD::run, cabanamd_impl.h:285-399), and no
+    rebuild or thermo step ever lands inside a stretch."""
+    from cabanamd_b200.harness import Simulation
+
+    seqs = []
+    for batch in (False, True):
+        sim = Simulation.__new__(Simulation)
+        sim.ctx = _Recorder()
+        sim.half, sim.rn, sim.exchange_rate = half, 2.8, 20
+        sim.guess, sim.layout, sim.step, sim.N = 50, 0, 13, 100  # starts mid-period
+        sim.mvv2e, sim.boltz, sim.thermo, sim.fuse_energy, sim.nranks = 1.0, 1.0, [], True, 1
+        sim.run(nsteps, thermo, batch=batch)
+        assert sim.step == 13 + nsteps
+        seqs.append(sim.ctx.calls)
+    stepwise, batched = seqs
+    assert _expand(batched, half) == stepwise
+    if nsteps > 3 and thermo != 1:
+        assert any(c[0] == "md_steps" for c in batched)
+    assert all(c[1] >= 1 for c in batched if c[0] == "md_steps")
