@@ -2,8 +2,10 @@
 // 6-phase ghost build, per-step ghost refresh and reverse force accumulation.
 // Replaces Comm<t_System> (reference src/comm_mpi.h:125-353, src/comm_mpi_impl.h:52-441)
 // and the [Cabana] Distributor/migrate + Halo/gather/scatter it delegates to.  MPI is
-// replaced by NCCL send/recv groups (one process per GPU); a phase whose face
-// neighbour is this rank itself (one rank in that dimension) is a local copy.
+// replaced by NCCL send/recv groups (one process per GPU) or, between several contexts of
+// one process, by the in-process hub (cbmd_hub_create; struct Xfer below is the one place
+// that knows the difference); a phase whose face neighbour is this rank itself (one rank
+// in that dimension) is a local copy.
 //
 // The six phases (+x,-x,+y,-y,+z,-z) are kept exactly — including forwarding of
 // earlier-phase ghosts and the odd-phase exclusion of the ghosts just received
